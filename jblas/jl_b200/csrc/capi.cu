@@ -1,0 +1,619 @@
+// capi.cu -- the C ABI of libjblas_b200.so (see include/jblas_b200.h) and the host-side planner.
+//
+// Host side of the replacement for jmul! (src/gemm.jl:244-348): where the reference's generator body picks a
+// register tile (pick_kernel_size, src/gemm.jl:258) and emits the two tile loops, this file picks a CTA tile
+// and kernel family per shape (plan()) and launches one grid whose 1-D block index is rasterised over the
+// tile grid.  No CPU fallback exists anywhere in this file.
+#include "../../../include/jblas_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "aux_kernels.cuh"
+#include "gemm_dmma.cuh"
+#include "gemm_simt.cuh"
+
+using namespace jb;
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(_e == cudaErrorMemoryAllocation ? JBLAS_B200_ENOMEM : JBLAS_B200_ECUDA,       \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// context (one per process: one process per GPU)
+// ---------------------------------------------------------------------------------------------------------
+struct Context {
+    int device = -1;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_stream = nullptr;  // H2D/D2H for the host-pointer entry points
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+    void* ws[3] = {nullptr, nullptr, nullptr};  // device staging for D, A, X (host-pointer entry points)
+    size_t ws_bytes[3] = {0, 0, 0};
+    float last_ms = 0.f;
+    bool attrs_set = false;
+};
+static Context g_ctx;
+static std::mutex g_mu;  // calls are serialised per context (SURVEY 8b "Threading")
+static std::atomic<int64_t> g_launches{0};
+
+static int require_init()
+{
+    if (g_ctx.device < 0) return fail(JBLAS_B200_ENOTINIT, "jblas_b200_init has not been called (no CPU fallback exists)");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel registry
+// ---------------------------------------------------------------------------------------------------------
+enum Family { FAM_SIMT = 0, FAM_DMMA = 1 };
+
+struct KernelInfo {
+    const char* name;
+    int dtype;   // JBLAS_B200_DT_*
+    int family;  // Family
+    int bm, bn, bk, stages, threads;
+    size_t smem;
+    float eff;  // relative per-tile efficiency used by the planner (1.0 = the big tile)
+    // launchers indexed [aligned][acc]
+    void (*launch[2][2])(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda,
+                         int64_t ldx, int tiles_m, int tiles_n, int group_m, cudaStream_t s);
+    cudaError_t (*set_attr)();
+};
+
+template <typename T, typename Cfg, bool ALIGNED, bool ACC>
+static void launch_simt(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                        int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+{
+    gemm_simt_kernel<T, Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
+        (T*)D, (const T*)A, (const T*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m);
+}
+template <typename T, typename Cfg>
+static cudaError_t attr_simt()
+{
+    cudaError_t e;
+#define SET(AL, AC)                                                                                               \
+    e = cudaFuncSetAttribute(gemm_simt_kernel<T, Cfg, AL, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                             (int)Cfg::SMEM);                                                                     \
+    if (e != cudaSuccess) return e;
+    SET(false, false) SET(false, true) SET(true, false) SET(true, true)
+#undef SET
+    return cudaSuccess;
+}
+template <typename Cfg, bool ALIGNED, bool ACC>
+static void launch_dmma(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                        int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+{
+    gemm_dmma_kernel<Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
+        (double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m);
+}
+template <typename Cfg>
+static cudaError_t attr_dmma()
+{
+    cudaError_t e;
+#define SET(AL, AC)                                                                                               \
+    e = cudaFuncSetAttribute(gemm_dmma_kernel<Cfg, AL, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                             (int)Cfg::SMEM);                                                                     \
+    if (e != cudaSuccess) return e;
+    SET(false, false) SET(false, true) SET(true, false) SET(true, true)
+#undef SET
+    return cudaSuccess;
+}
+
+#define SIMT_ENTRY(NAME, T, DT, CFG, EFF)                                                                          \
+    {                                                                                                              \
+        NAME, DT, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,                  \
+            {{launch_simt<T, CFG, false, false>, launch_simt<T, CFG, false, true>},                                \
+             {launch_simt<T, CFG, true, false>, launch_simt<T, CFG, true, true>}},                                 \
+            attr_simt<T, CFG>                                                                                      \
+    }
+#define DMMA_ENTRY(NAME, CFG, EFF)                                                                                 \
+    {                                                                                                              \
+        NAME, JBLAS_B200_DT_F64, FAM_DMMA, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
+            {{launch_dmma<CFG, false, false>, launch_dmma<CFG, false, true>},                                      \
+             {launch_dmma<CFG, true, false>, launch_dmma<CFG, true, true>}},                                       \
+            attr_dmma<CFG>                                                                                         \
+    }
+
+//                         T      WM WN BK ST MINB
+using S64_128x128 = SimtCfg<double, 2, 4, 16, 4, 1>;
+using S64_128x64 = SimtCfg<double, 2, 2, 16, 4, 1>;
+using S64_64x64 = SimtCfg<double, 1, 2, 16, 4, 1>;
+using S32_128x128 = SimtCfg<float, 2, 4, 16, 4, 2>;
+using S32_128x64 = SimtCfg<float, 2, 2, 16, 4, 2>;
+using S32_64x64 = SimtCfg<float, 1, 2, 16, 4, 4>;
+using D64_128x128 = DmmaCfg<2, 4, 16, 4>;
+using D64_128x64 = DmmaCfg<2, 2, 16, 4>;
+using D64_64x64 = DmmaCfg<1, 2, 16, 4>;
+
+static const KernelInfo g_kernels[] = {
+    /* 0 */ SIMT_ENTRY("simt_f64_128x128x16", double, JBLAS_B200_DT_F64, S64_128x128, 1.00f),
+    /* 1 */ SIMT_ENTRY("simt_f64_128x64x16", double, JBLAS_B200_DT_F64, S64_128x64, 0.95f),
+    /* 2 */ SIMT_ENTRY("simt_f64_64x64x16", double, JBLAS_B200_DT_F64, S64_64x64, 0.85f),
+    /* 3 */ DMMA_ENTRY("dmma_f64_128x128x16", D64_128x128, 1.00f),
+    /* 4 */ DMMA_ENTRY("dmma_f64_128x64x16", D64_128x64, 0.95f),
+    /* 5 */ DMMA_ENTRY("dmma_f64_64x64x16", D64_64x64, 0.85f),
+    /* 6 */ SIMT_ENTRY("simt_f32_128x128x16", float, JBLAS_B200_DT_F32, S32_128x128, 1.00f),
+    /* 7 */ SIMT_ENTRY("simt_f32_128x64x16", float, JBLAS_B200_DT_F32, S32_128x64, 0.95f),
+    /* 8 */ SIMT_ENTRY("simt_f32_64x64x16", float, JBLAS_B200_DT_F32, S32_64x64, 0.85f),
+};
+static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
+#define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
+
+// ---------------------------------------------------------------------------------------------------------
+// planner: the B200 counterpart of pick_kernel_size + blocking_structure
+// ---------------------------------------------------------------------------------------------------------
+struct Plan {
+    int kidx;
+    int tiles_m, tiles_n, group_m;
+    bool aligned;
+};
+
+static bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldx, const void* A, const void* X,
+                     int selector, Plan* out)
+{
+    (void)K;
+    const int num_sms = g_ctx.num_sms > 0 ? g_ctx.num_sms : 148;
+    int family = -1, explicit_idx = -1;
+    if (selector >= JBLAS_B200_EXPLICIT_BASE) {
+        explicit_idx = selector - JBLAS_B200_EXPLICIT_BASE;
+        if (explicit_idx >= NUM_KERNELS || g_kernels[explicit_idx].dtype != dtype)
+            return fail(JBLAS_B200_EINVAL, "explicit kernel selector %d is not a %s kernel", selector,
+                        dtype == JBLAS_B200_DT_F64 ? "Float64" : "Float32");
+    } else if (dtype == JBLAS_B200_DT_F64) {
+        if (selector == JBLAS_B200_F64_AUTO) family = FAM_DMMA;  // see DESIGN.md "kernel choice" (ncu evidence)
+        else if (selector == JBLAS_B200_F64_DMMA) family = FAM_DMMA;
+        else if (selector == JBLAS_B200_F64_SIMT) family = FAM_SIMT;
+        else return fail(JBLAS_B200_EINVAL, "unknown Float64 kernel selector %d", selector);
+    } else {
+        if (selector == JBLAS_B200_F32_EXACT) family = FAM_SIMT;
+        else if (selector == JBLAS_B200_F32_3XTF32)
+            return fail(JBLAS_B200_EUNSUPPORTED, "3xTF32 tcgen05 path is not built in this version");
+        else return fail(JBLAS_B200_EINVAL, "unknown Float32 mode selector %d", selector);
+    }
+    int best = -1;
+    double best_t = 0;
+    for (int i = 0; i < NUM_KERNELS; ++i) {
+        const KernelInfo& k = g_kernels[i];
+        if (explicit_idx >= 0 ? (i != explicit_idx) : (k.dtype != dtype || k.family != family)) continue;
+        int64_t tiles = ((M + k.bm - 1) / k.bm) * ((N + k.bn - 1) / k.bn);
+        double per_tile = (double)k.bm * k.bn;
+        double waves = (double)((tiles + num_sms - 1) / num_sms);
+        int warps = k.threads / 32;
+        double t = waves * per_tile;
+        double single = per_tile * 4.0 / (warps < 4 ? warps : 4);  // a lone CTA with <4 warps cannot fill an SM
+        if (single > t) t = single;
+        t /= k.eff;
+        if (best < 0 || t < best_t) { best = i; best_t = t; }
+    }
+    if (best < 0) return fail(JBLAS_B200_EUNSUPPORTED, "no kernel for this dtype/selector");
+    const KernelInfo& k = g_kernels[best];
+    out->kidx = best;
+    out->tiles_m = (int)((M + k.bm - 1) / k.bm);
+    out->tiles_n = (int)((N + k.bn - 1) / k.bn);
+    // raster group: keep ~sqrt(#SMs) tile rows together so a resident wave touches a near-square block
+    out->group_m = out->tiles_m < 12 ? out->tiles_m : 12;
+    if (out->group_m < 1) out->group_m = 1;
+    const int vec = dtype == JBLAS_B200_DT_F64 ? 2 : 4;
+    out->aligned = is_aligned16(A) && is_aligned16(X) && (lda % vec == 0) && (ldx % vec == 0);
+    return 0;
+}
+
+static int validate(const void* D, const void* A, const void* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
+                    int64_t ldx)
+{
+    if (M < 0 || K < 0 || N < 0) return fail(JBLAS_B200_EINVAL, "negative dimension (M=%lld K=%lld N=%lld)", (long long)M, (long long)K, (long long)N);
+    if (M > 0x7fffffffLL - 256 || N > 0x7fffffffLL - 256 || K > 0x7fffffffLL - 256)
+        return fail(JBLAS_B200_EINVAL, "dimension exceeds 2^31-257");
+    if (M == 0 || N == 0) return 0;
+    if (!D) return fail(JBLAS_B200_EINVAL, "D is NULL");
+    if (ldd < M) return fail(JBLAS_B200_EINVAL, "ldd=%lld < M=%lld", (long long)ldd, (long long)M);
+    if (K > 0) {
+        if (!A || !X) return fail(JBLAS_B200_EINVAL, "A or X is NULL");
+        if (lda < M) return fail(JBLAS_B200_EINVAL, "lda=%lld < M=%lld", (long long)lda, (long long)M);
+        if (ldx < K) return fail(JBLAS_B200_EINVAL, "ldx=%lld < K=%lld", (long long)ldx, (long long)K);
+    }
+    return 0;
+}
+
+template <typename T>
+__global__ void zero_fill_kernel(T* D, int64_t M, int64_t N, int64_t ldd)
+{
+    int64_t total = M * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        D[(i / M) * ldd + (i % M)] = T(0);
+}
+
+static int set_all_attrs()
+{
+    if (g_ctx.attrs_set) return 0;
+    for (int i = 0; i < NUM_KERNELS; ++i) CUDA_TRY(g_kernels[i].set_attr());
+    g_ctx.attrs_set = true;
+    return 0;
+}
+
+template <typename T>
+static int gemm_dev(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
+                    int64_t ldx, int accumulate, int selector, cudaStream_t s)
+{
+    if (int rc = require_init()) return rc;
+    if (int rc = validate(D, A, X, M, K, N, ldd, lda, ldx)) return rc;
+    if (M == 0 || N == 0) return 0;
+    if (!s) s = g_ctx.stream;
+    if (K == 0) {  // empty contraction: jmul! would read X[1,j] out of bounds; defined here as D = 0 (or D unchanged)
+        if (!accumulate) {
+            zero_fill_kernel<T><<<g_ctx.num_sms * 4, 256, 0, s>>>(D, M, N, ldd);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        return 0;
+    }
+    Plan p;
+    if (int rc = make_plan(dtype, M, K, N, lda, ldx, A, X, selector, &p)) return rc;
+    if (int rc = set_all_attrs()) return rc;
+    const KernelInfo& k = g_kernels[p.kidx];
+    k.launch[p.aligned ? 1 : 0][accumulate ? 1 : 0](D, A, X, (int)M, (int)N, (int)K, ldd, lda, ldx, p.tiles_m, p.tiles_n,
+                                                    p.group_m, s);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-pointer path
+// ---------------------------------------------------------------------------------------------------------
+static int ensure_ws(int i, size_t bytes)
+{
+    if (g_ctx.ws_bytes[i] >= bytes) return 0;
+    if (g_ctx.ws[i]) { cudaFree(g_ctx.ws[i]); g_ctx.ws[i] = nullptr; g_ctx.ws_bytes[i] = 0; }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&g_ctx.ws[i], want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&g_ctx.ws[i], want);
+    }
+    if (e != cudaSuccess) return fail(JBLAS_B200_ENOMEM, "device workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    g_ctx.ws_bytes[i] = want;
+    return 0;
+}
+
+// Synchronous host-pointer GEMM: the literal drop-in for jmul!(D, A, X).
+//   copy stream : X (all), then A in K-panels           (H2D)
+//   compute     : panel p multiplies A[:, kp] * X[kp, :] into the device D with accumulate = (p > 0) -- ascending
+//                 k per element, so the chain (and the bits) are those of a single launch
+//   copy stream : D back by column blocks               (D2H)
+template <typename T>
+static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
+                     int64_t ldx, int accumulate, int selector)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = require_init()) return rc;
+    if (int rc = validate(D, A, X, M, K, N, ldd, lda, ldx)) return rc;
+    if (M == 0 || N == 0) return 0;
+    const size_t es = sizeof(T);
+    // device copies are dense with even leading dimensions so the 16-byte staging path applies
+    const int vec = 16 / (int)es;
+    const int64_t dM = (M + vec - 1) / vec * vec, dK = (K + vec - 1) / vec * vec;
+    if (int rc = ensure_ws(0, (size_t)dM * N * es)) return rc;
+    if (K > 0) {
+        if (int rc = ensure_ws(1, (size_t)dM * K * es)) return rc;
+        if (int rc = ensure_ws(2, (size_t)dK * N * es)) return rc;
+    }
+    T* dD = (T*)g_ctx.ws[0];
+    T* dA = (T*)g_ctx.ws[1];
+    T* dX = (T*)g_ctx.ws[2];
+    cudaStream_t cs = g_ctx.copy_stream, ks = g_ctx.stream;
+    CUDA_TRY(cudaEventRecord(g_ctx.ev0, cs));
+    if (accumulate) CUDA_TRY(cudaMemcpy2DAsync(dD, dM * es, D, ldd * es, M * es, N, cudaMemcpyHostToDevice, cs));
+    if (K > 0) CUDA_TRY(cudaMemcpy2DAsync(dX, dK * es, X, ldx * es, K * es, N, cudaMemcpyHostToDevice, cs));
+    // K-panels of A: big enough to amortise launches, small enough to overlap PCIe with compute
+    int64_t kp = K;
+    if ((size_t)M * K * es > ((size_t)64 << 20)) {
+        kp = (int64_t)(((size_t)64 << 20) / ((size_t)M * es));
+        kp = kp / 64 * 64;
+        if (kp < 64) kp = 64;
+    }
+    if (K == 0) {
+        if (int rc = gemm_dev<T>(dtype, dD, dA, dX, M, 0, N, dM, dM, dK > 0 ? dK : 1, accumulate, selector, ks)) return rc;
+    }
+    for (int64_t k0 = 0; k0 < K; k0 += kp) {
+        int64_t kc = (K - k0 < kp) ? (K - k0) : kp;
+        CUDA_TRY(cudaMemcpy2DAsync(dA + k0 * dM, dM * es, A + k0 * lda, lda * es, M * es, kc, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
+        CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
+        if (int rc = gemm_dev<T>(dtype, dD, dA + k0 * dM, dX + k0, M, kc, N, dM, dM, dK, (accumulate || k0 > 0) ? 1 : 0,
+                                 selector, ks))
+            return rc;
+    }
+    CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
+    CUDA_TRY(cudaStreamWaitEvent(cs, g_ctx.ev_copy, 0));
+    CUDA_TRY(cudaMemcpy2DAsync(D, ldd * es, dD, dM * es, M * es, N, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaEventRecord(g_ctx.ev1, cs));
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    CUDA_TRY(cudaStreamSynchronize(ks));
+    cudaEventElapsedTime(&g_ctx.last_ms, g_ctx.ev0, g_ctx.ev1);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// exported C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int jblas_b200_version(void) { return JBLAS_B200_VERSION; }
+const char* jblas_b200_last_error(void) { return g_err; }
+
+int jblas_b200_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(JBLAS_B200_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+int jblas_b200_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.device == device) return 0;
+    if (g_ctx.device >= 0) return fail(JBLAS_B200_EINVAL, "already initialised on device %d (one process per GPU)", g_ctx.device);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(JBLAS_B200_ECUDA, "no CUDA device available (%s); jblas_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n) return fail(JBLAS_B200_EINVAL, "device %d out of range [0,%d)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(JBLAS_B200_EUNSUPPORTED, "device %d is sm_%d%d; this library contains sm_100a code only", device,
+                    prop.major, prop.minor);
+    g_ctx.num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&g_ctx.ev0));
+    CUDA_TRY(cudaEventCreate(&g_ctx.ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_copy, cudaEventDisableTiming));
+    g_ctx.device = device;
+    g_ctx.attrs_set = false;
+    return set_all_attrs();
+}
+
+int jblas_b200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.device < 0) return 0;
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 3; ++i) {
+        if (g_ctx.ws[i]) cudaFree(g_ctx.ws[i]);
+        g_ctx.ws[i] = nullptr;
+        g_ctx.ws_bytes[i] = 0;
+    }
+    if (g_ctx.ev0) cudaEventDestroy(g_ctx.ev0);
+    if (g_ctx.ev1) cudaEventDestroy(g_ctx.ev1);
+    if (g_ctx.ev_copy) cudaEventDestroy(g_ctx.ev_copy);
+    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
+    g_ctx = Context();
+    return 0;
+}
+
+int jblas_b200_gemm_f64_dev(double* D, const double* A, const double* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
+                            int64_t lda, int64_t ldx, int accumulate, int kernel, void* stream)
+{
+    return gemm_dev<double>(JBLAS_B200_DT_F64, D, A, X, M, K, N, ldd, lda, ldx, accumulate, kernel, (cudaStream_t)stream);
+}
+int jblas_b200_gemm_f32_dev(float* D, const float* A, const float* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
+                            int64_t lda, int64_t ldx, int accumulate, int mode, void* stream)
+{
+    return gemm_dev<float>(JBLAS_B200_DT_F32, D, A, X, M, K, N, ldd, lda, ldx, accumulate, mode, (cudaStream_t)stream);
+}
+int jblas_b200_gemm_f64(double* D, const double* A, const double* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
+                        int64_t lda, int64_t ldx, int accumulate, int kernel)
+{
+    return gemm_host<double>(JBLAS_B200_DT_F64, D, A, X, M, K, N, ldd, lda, ldx, accumulate, kernel);
+}
+int jblas_b200_gemm_f32(float* D, const float* A, const float* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
+                        int64_t lda, int64_t ldx, int accumulate, int mode)
+{
+    return gemm_host<float>(JBLAS_B200_DT_F32, D, A, X, M, K, N, ldd, lda, ldx, accumulate, mode);
+}
+
+// jBLAS naming: D is MxP, A is MxN, X is NxP (src/gemm.jl:244); dense MMatrix storage.
+int jblas_b200_jmul_f64(double* D, const double* A, const double* X, int64_t M, int64_t N, int64_t P)
+{
+    return gemm_host<double>(JBLAS_B200_DT_F64, D, A, X, M, N, P, M > 0 ? M : 1, M > 0 ? M : 1, N > 0 ? N : 1, 0,
+                             JBLAS_B200_F64_AUTO);
+}
+int jblas_b200_jmul_f32(float* D, const float* A, const float* X, int64_t M, int64_t N, int64_t P)
+{
+    return gemm_host<float>(JBLAS_B200_DT_F32, D, A, X, M, N, P, M > 0 ? M : 1, M > 0 ? M : 1, N > 0 ? N : 1, 0,
+                            JBLAS_B200_F32_EXACT);
+}
+// fastmul! (src/kernels.jl:202-208): small static matrices, any M (row remainder masked in the reference).
+// Small products are issue/latency bound either way; the exact SIMT kernels with predicated edges serve them.
+int jblas_b200_fastmul_f64(double* D, const double* A, const double* X, int64_t M, int64_t N, int64_t P)
+{
+    return gemm_host<double>(JBLAS_B200_DT_F64, D, A, X, M, N, P, M > 0 ? M : 1, M > 0 ? M : 1, N > 0 ? N : 1, 0,
+                             JBLAS_B200_F64_SIMT);
+}
+int jblas_b200_fastmul_f32(float* D, const float* A, const float* X, int64_t M, int64_t N, int64_t P)
+{
+    return gemm_host<float>(JBLAS_B200_DT_F32, D, A, X, M, N, P, M > 0 ? M : 1, M > 0 ? M : 1, N > 0 ? N : 1, 0,
+                            JBLAS_B200_F32_EXACT);
+}
+// kernel!/initkernel! (src/kernels.jl:239,273): stride_AD is shared by A and D (src/kernels.jl:213-215).
+// The reference throws unless Mk is a multiple of the vector width (src/kernels.jl:219,249); here any Mk works.
+int jblas_b200_kernel_f64(double* pD, const double* pA, const double* pX, int64_t Mk, int64_t Pk, int64_t stride_AD,
+                          int64_t stride_X, int64_t N)
+{
+    return gemm_host<double>(JBLAS_B200_DT_F64, pD, pA, pX, Mk, N, Pk, stride_AD, stride_AD, stride_X, 1, JBLAS_B200_F64_SIMT);
+}
+int jblas_b200_initkernel_f64(double* pD, const double* pA, const double* pX, int64_t Mk, int64_t Pk, int64_t stride_AD,
+                              int64_t stride_X, int64_t N)
+{
+    return gemm_host<double>(JBLAS_B200_DT_F64, pD, pA, pX, Mk, N, Pk, stride_AD, stride_AD, stride_X, 0, JBLAS_B200_F64_SIMT);
+}
+int jblas_b200_kernel_f32(float* pD, const float* pA, const float* pX, int64_t Mk, int64_t Pk, int64_t stride_AD,
+                          int64_t stride_X, int64_t N)
+{
+    return gemm_host<float>(JBLAS_B200_DT_F32, pD, pA, pX, Mk, N, Pk, stride_AD, stride_AD, stride_X, 1, JBLAS_B200_F32_EXACT);
+}
+int jblas_b200_initkernel_f32(float* pD, const float* pA, const float* pX, int64_t Mk, int64_t Pk, int64_t stride_AD,
+                              int64_t stride_X, int64_t N)
+{
+    return gemm_host<float>(JBLAS_B200_DT_F32, pD, pA, pX, Mk, N, Pk, stride_AD, stride_AD, stride_X, 0, JBLAS_B200_F32_EXACT);
+}
+
+int jblas_b200_alloc(void** dptr, size_t bytes)
+{
+    if (int rc = require_init()) return rc;
+    if (!dptr) return fail(JBLAS_B200_EINVAL, "dptr is NULL");
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(JBLAS_B200_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return 0;
+}
+int jblas_b200_free(void* dptr)
+{
+    if (int rc = require_init()) return rc;
+    CUDA_TRY(cudaFree(dptr));
+    return 0;
+}
+int jblas_b200_h2d(void* dst, const void* src, size_t bytes)
+{
+    if (int rc = require_init()) return rc;
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int jblas_b200_d2h(void* dst, const void* src, size_t bytes)
+{
+    if (int rc = require_init()) return rc;
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int jblas_b200_host_register(void* host, size_t bytes)
+{
+    if (int rc = require_init()) return rc;
+    CUDA_TRY(cudaHostRegister(host, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+int jblas_b200_host_unregister(void* host)
+{
+    if (int rc = require_init()) return rc;
+    CUDA_TRY(cudaHostUnregister(host));
+    return 0;
+}
+int jblas_b200_stream_sync(void* stream)
+{
+    if (int rc = require_init()) return rc;
+    CUDA_TRY(cudaStreamSynchronize(stream ? (cudaStream_t)stream : g_ctx.stream));
+    return 0;
+}
+
+int jblas_b200_randn_fill(void* dptr, int64_t first, int64_t n, uint64_t seed, int dtype, void* stream)
+{
+    if (int rc = require_init()) return rc;
+    if (n < 0 || first < 0 || (n > 0 && !dptr)) return fail(JBLAS_B200_EINVAL, "bad randn_fill arguments");
+    if (n == 0) return 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : g_ctx.stream;
+    int blocks = g_ctx.num_sms * 8;
+    if (dtype == JBLAS_B200_DT_F64)
+        randn_fill_kernel<double><<<blocks, 256, 0, s>>>((double*)dptr, first, n, seed);
+    else if (dtype == JBLAS_B200_DT_F32)
+        randn_fill_kernel<float><<<blocks, 256, 0, s>>>((float*)dptr, first, n, seed);
+    else
+        return fail(JBLAS_B200_EINVAL, "unknown dtype %d", dtype);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int jblas_b200_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda, int64_t ldx, int selector,
+                    int64_t out[10])
+{
+    if (!out) return fail(JBLAS_B200_EINVAL, "out is NULL");
+    if (dtype != JBLAS_B200_DT_F64 && dtype != JBLAS_B200_DT_F32) return fail(JBLAS_B200_EINVAL, "unknown dtype %d", dtype);
+    if (M <= 0 || N <= 0 || K <= 0 || ldd < M || lda < M || ldx < K) return fail(JBLAS_B200_EINVAL, "bad dimensions");
+    Plan p;
+    // alignment of device bases is assumed (cudaMalloc gives 256 B); leading dimensions decide the staging path
+    if (int rc = make_plan(dtype, M, K, N, lda, ldx, nullptr, nullptr, selector, &p)) return rc;
+    const KernelInfo& k = g_kernels[p.kidx];
+    out[0] = p.kidx; out[1] = k.bm; out[2] = k.bn; out[3] = k.bk; out[4] = k.stages; out[5] = k.threads;
+    out[6] = (int64_t)p.tiles_m * p.tiles_n; out[7] = p.group_m; out[8] = (int64_t)k.smem; out[9] = p.aligned ? 1 : 0;
+    return 0;
+}
+const char* jblas_b200_kernel_name(int kidx) { return (kidx >= 0 && kidx < NUM_KERNELS) ? g_kernels[kidx].name : ""; }
+int jblas_b200_num_kernels(void) { return NUM_KERNELS; }
+
+int64_t jblas_b200_launch_count(void) { return g_launches.load(); }
+float jblas_b200_time_last_ms(void) { return g_ctx.last_ms; }
+
+int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms_out)
+{
+    if (int rc = require_init()) return rc;
+    if (iters <= 0 || !tflops) return fail(JBLAS_B200_EINVAL, "bad probe arguments");
+    cudaStream_t s = g_ctx.stream;
+    void* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, 256));
+    const int blocks = g_ctx.num_sms * 4, threads = 256;
+    double flops = 0;
+    for (int rep = 0; rep < 2; ++rep) {  // rep 0 = warm-up
+        CUDA_TRY(cudaEventRecord(g_ctx.ev0, s));
+        if (kind == 0) {
+            probe_dfma_kernel<16><<<blocks, threads, 0, s>>>((double*)out, iters, 1.0000001, 1e-9);
+            flops = 2.0 * 16 * iters * (double)blocks * threads;
+        } else if (kind == 1) {
+            probe_dmma_kernel<16><<<blocks, threads, 0, s>>>((double*)out, iters, 1.0000001, 1e-9);
+            flops = 2.0 * 256 * 16 * iters * (double)blocks * (threads / 32);
+        } else if (kind == 2) {
+            probe_ffma_kernel<32><<<blocks, threads, 0, s>>>((float*)out, iters, 1.0000001f, 1e-9f);
+            flops = 2.0 * 32 * iters * (double)blocks * threads;
+        } else {
+            cudaFree(out);
+            return fail(JBLAS_B200_EINVAL, "unknown probe kind %d", kind);
+        }
+        g_launches++;
+        CUDA_TRY(cudaEventRecord(g_ctx.ev1, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_ctx.ev0, g_ctx.ev1));
+    CUDA_TRY(cudaFree(out));
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return 0;
+}
+
+}  // extern "C"

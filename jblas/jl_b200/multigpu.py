@@ -1,0 +1,120 @@
+"""Single-node multi-GPU mode of the jmul! path: one process per GPU (torch.distributed, NCCL over NVLink).
+
+Partition.  D = A*X is sharded by COLUMN BLOCKS of D and X -- exactly the outer `cc` loop of the
+reference's jmul! (src/gemm.jl:313): column block j of D depends only on column block j of X and on all of A.
+Column blocks are contiguous in column-major storage, so shards are born and stay on their GPU; there is no
+reduction and no gather.  The one real exchange step is making A visible everywhere: rank `root` owns A and
+broadcasts it once per product.
+
+Pipeline.  A is broadcast in K-PANELS (a column panel A[:, k0:k1] of a column-major matrix is one contiguous
+M*(k1-k0) block) on the NCCL stream while the local GEMM consumes earlier panels:
+    panel p arrives  ->  D_shard (+)= A[:, kp] * X_shard[kp, :]      accumulate = (p > 0)
+The accumulate pass has the reference's kernel! semantics (src/kernels.jl:226): each element's chain stays
+ascending in k across panels, so an N-GPU result is bit-identical to the 1-GPU result with the exact kernels.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+
+def column_shard(n_cols: int, world: int, rank: int) -> tuple[int, int]:
+    """[c0, c1) of the columns of X and D owned by `rank`; remainder columns go to the last ranks."""
+    if world < 1 or not (0 <= rank < world) or n_cols < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(n_cols, world)
+    counts = [base + (1 if r >= world - rem else 0) for r in range(world)]
+    c0 = sum(counts[:rank])
+    return c0, c0 + counts[rank]
+
+
+def k_panels(K: int, panel_k: int) -> list[tuple[int, int]]:
+    """K split into [k0, k1) panels of `panel_k` (multiple of 64 keeps 16-byte staging and full k-tiles)."""
+    if panel_k <= 0:
+        raise ValueError("panel_k must be positive")
+    if panel_k % 64:
+        raise ValueError("panel_k must be a multiple of 64")
+    return [(k0, min(k0 + panel_k, K)) for k0 in range(0, max(K, 0), panel_k)] or [(0, 0)]
+
+
+def _default_local_gemm(D, A, X, accumulate: bool, kernel):
+    from . import api
+
+    return api._gemm(D, A, X, accumulate, kernel)  # the CUDA path; raises if the library / GPU is missing
+
+
+class ShardedGemm:
+    """D_shard = A * X_shard on every rank, A broadcast from `root` in K panels overlapped with compute.
+
+    All matrices are column-major torch tensors (strides (1, ld)).  `A` must be an M x K buffer on every rank;
+    its contents matter on `root` only and are overwritten elsewhere.  `local_gemm(D, A, X, accumulate, kernel)`
+    is injectable so the host logic (partition, panel schedule, ordering) can be exercised on CPU with the gloo
+    backend; the default is the CUDA kernel path and there is no automatic fallback.
+    """
+
+    def __init__(self, M: int, K: int, n_cols_total: int, group=None, root: int = 0, panel_k: int = 2048,
+                 kernel: Optional[int] = None, local_gemm: Optional[Callable] = None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.root = root
+        self.M, self.K, self.n_total = M, K, n_cols_total
+        self.c0, self.c1 = column_shard(n_cols_total, self.world, self.rank)
+        self.panels = k_panels(K, panel_k) if self.world > 1 else [(0, K)]
+        self.kernel = kernel
+        self.local_gemm = local_gemm or _default_local_gemm
+        self._comm_stream = None
+
+    @property
+    def shard_cols(self) -> int:
+        return self.c1 - self.c0
+
+    def _panel(self, A, k0, k1):
+        return A[:, k0:k1]
+
+    def _panel_wire(self, A, k0, k1):
+        # A is dense column-major M x K: columns k0..k1 are ONE contiguous block; its transpose is the row-major
+        # contiguous (k1-k0, M) tensor torch.distributed wants on the wire (same bytes, no copy)
+        return A[:, k0:k1].t()
+
+    def __call__(self, D_shard, A, X_shard):
+        import torch
+
+        M, K = self.M, self.K
+        if tuple(A.shape) != (M, K) or tuple(X_shard.shape) != (K, self.shard_cols) or tuple(D_shard.shape) != (M, self.shard_cols):
+            raise ValueError(f"shape mismatch: A {tuple(A.shape)}, X shard {tuple(X_shard.shape)}, D shard {tuple(D_shard.shape)}; "
+                             f"expected ({M},{K}), ({K},{self.shard_cols}), ({M},{self.shard_cols})")
+        if self.world == 1:
+            self.local_gemm(D_shard, A, X_shard, False, self.kernel)
+            return D_shard
+        if not A.t().is_contiguous():
+            raise ValueError("A must be dense column-major (leading dimension == M) to be broadcast in K panels")
+        cuda = A.is_cuda
+        works = []
+        if cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=A.device)
+            compute = torch.cuda.current_stream(A.device)
+            self._comm_stream.wait_stream(compute)  # A (on root) / the receive buffer (elsewhere) must be ready
+            with torch.cuda.stream(self._comm_stream):
+                for k0, k1 in self.panels:
+                    works.append(self.dist.broadcast(self._panel_wire(A, k0, k1), src=self.root, group=self.group, async_op=True))
+        else:
+            for k0, k1 in self.panels:
+                works.append(self.dist.broadcast(self._panel_wire(A, k0, k1), src=self.root, group=self.group, async_op=True))
+        for p, (k0, k1) in enumerate(self.panels):
+            if cuda:
+                with torch.cuda.stream(self._comm_stream):
+                    works[p].wait()  # orders the NCCL work before what follows on the comm stream
+                    ev = torch.cuda.Event()
+                    ev.record(self._comm_stream)
+                torch.cuda.current_stream(A.device).wait_event(ev)
+            else:
+                works[p].wait()
+            self.local_gemm(D_shard, self._panel(A, k0, k1), X_shard[k0:k1, :], p > 0, self.kernel)
+        return D_shard
+
+    def launches_per_call(self) -> int:
+        return len(self.panels)

@@ -1,0 +1,355 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar (north_star / SURVEY 8c):
+  * exact kernels (SIMT DFMA / FFMA)  : BIT-IDENTICAL to the oracle chain (product, then ascending-k fma);
+  * DMMA tensor path                  : |D - D_oracle|_ij <= 2*K*eps*(|A||X|)_ij, eps = 2^-52;
+  * edges are computed (the reference skips them), D prefilled with a NaN sentinel catches unwritten elements.
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tests.helpers import SEED_A, SEED_X, bits_equal, nan_f, randn_f, to_dev, to_host
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _exact_selectors(jb, dt):
+    names = jb.kernel_names()
+    tag = "simt_f64" if dt == np.float64 else "simt_f32"
+    return [jb.EXPLICIT_BASE + i for i, n in enumerate(names) if n.startswith(tag)]
+
+
+def _dmma_selectors(jb):
+    return [jb.EXPLICIT_BASE + i for i, n in enumerate(jb.kernel_names()) if n.startswith("dmma_f64")]
+
+
+def _run_dev(jb, A, X, kernel, accumulate_into=None, ldd=None):
+    import torch
+
+    M, N = A.shape[0], X.shape[1]
+    Dh = nan_f((M, N), A.dtype, ld=ldd) if accumulate_into is None else accumulate_into.copy(order="F")
+    dD, dA, dX = to_dev(Dh), to_dev(A), to_dev(X)
+    if accumulate_into is None:
+        jb.jmul_(dD, dA, dX, kernel=kernel)
+    else:
+        from jblas.jl_b200 import api
+
+        api._gemm(dD, dA, dX, True, kernel)
+    torch.cuda.synchronize()
+    return to_host(dD)
+
+
+# ------------------------------------------------------------------------------------------------------
+# golden vectors
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_golden_vectors(jb, path):
+    g = np.load(path)
+    A, X, D = np.asfortranarray(g["A"]), np.asfortranarray(g["X"]), g["D"]
+    full = oracle.oracle_gemm(A, X)
+    for sel in _exact_selectors(jb, A.dtype.type):
+        got = _run_dev(jb, A, X, sel)
+        if "covered" in g:
+            r, c = (int(v) for v in g["covered"])
+            assert bits_equal(got[:r, :c], D[:r, :c])
+        else:
+            assert bits_equal(got, D)
+        assert bits_equal(got, full)  # remainder rows/cols are computed too (the reference leaves them untouched)
+    Dh = nan_f(D.shape, D.dtype)
+    jb.fastmul_(Dh, A, X)  # host-pointer entry (what a Julia ccall hits)
+    assert bits_equal(Dh, full)
+
+
+# ------------------------------------------------------------------------------------------------------
+# exact kernels: bit-identical
+# ------------------------------------------------------------------------------------------------------
+SHAPES = [
+    (1, 1, 1), (1, 7, 1), (3, 2, 5), (16, 32, 14), (32, 32, 28), (128, 128, 126), (800, 900, 840),  # ref script shapes
+    (64, 16, 64), (128, 16, 128), (129, 17, 127), (257, 33, 65), (255, 15, 129), (256, 256, 256), (130, 1000, 70),
+    (40, 3, 5), (1000, 1, 1000), (2, 3000, 3),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_exact_kernels_bit_identical(jb, shape, dt):
+    M, K, N = shape
+    A, X = randn_f((M, K), dt, SEED_A), randn_f((K, N), dt, SEED_X)
+    want = oracle.oracle_gemm(A, X)
+    for sel in _exact_selectors(jb, dt):
+        got = _run_dev(jb, A, X, sel)
+        assert not np.isnan(got).any(), "unwritten element (NaN sentinel survived)"
+        assert bits_equal(got, want), (jb.kernel_names()[sel - jb.EXPLICIT_BASE], shape)
+
+
+@pytest.mark.parametrize("lds", [(130, 131, 40), (129, 136, 33), (200, 129, 64), (144, 160, 48)], ids=str)
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_exact_kernels_strided_leading_dimensions(jb, lds, dt):
+    """Sub-matrix views: ld > rows, odd and even (both staging paths), untouched padding stays NaN."""
+    M, K, N = 129, 33, 37
+    lda, ldd, ldx = lds
+    A, X = randn_f((M, K), dt, SEED_A, ld=lda), randn_f((K, N), dt, SEED_X, ld=ldx)
+    want = oracle.oracle_gemm(np.asfortranarray(A), np.asfortranarray(X))
+    for sel in _exact_selectors(jb, dt):
+        import torch
+
+        Dh = nan_f((M, N), dt, ld=ldd)
+        dD, dA, dX = to_dev(Dh), to_dev(A), to_dev(X)
+        jb.jmul_(dD, dA, dX, kernel=sel)
+        torch.cuda.synchronize()
+        assert bits_equal(to_host(dD), want)
+        parent = dD.t().untyped_storage()  # the padding rows M..ldd-1 of every column must be untouched
+        full = torch.empty(0, dtype=dD.dtype, device=dD.device).set_(parent).view(N, ldd).cpu().numpy()
+        assert np.isnan(full[:, M:]).all()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_accumulate_is_kernel_bang_semantics(jb, dt):
+    """kernel!: D is loaded first and the chain continues (src/kernels.jl:226) -- bit-identical to the oracle."""
+    M, K, N = 200, 77, 90
+    A, X = randn_f((M, K), dt, SEED_A), randn_f((K, N), dt, SEED_X)
+    D0 = randn_f((M, N), dt, 99)
+    want = oracle.oracle_gemm(A, X, D0.copy(order="F"), accumulate=True)
+    for sel in _exact_selectors(jb, dt):
+        assert bits_equal(_run_dev(jb, A, X, sel, accumulate_into=D0), want)
+    # split-K by accumulate passes == one pass (the property the multi-GPU K-panel pipeline relies on)
+    one = oracle.oracle_gemm(A, X)
+    part = _run_dev(jb, np.asfortranarray(A[:, :40]), np.asfortranarray(X[:40, :]), _exact_selectors(jb, dt)[0])
+    two = _run_dev(jb, np.asfortranarray(A[:, 40:]), np.asfortranarray(X[40:, :]), _exact_selectors(jb, dt)[0], accumulate_into=part)
+    assert bits_equal(two, one)
+
+
+def test_special_values_follow_the_chain(jb):
+    M, K, N = 70, 37, 9
+    A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
+    A[0, :] = 0.0
+    X[:, 0] = -np.abs(X[:, 0])          # row 0 x col 0: every product is -0.0 -> result -0.0
+    A[1, :] = np.tile([1.0, -1.0], K)[:K]
+    X[:, 1] = 1.0                       # exact cancellation
+    A[2, 5] = np.inf
+    A[3, 6] = np.nan
+    A[4, :] *= 1e-160
+    X[:, 2] *= 1e-160                   # subnormal / underflowing products
+    want = oracle.oracle_gemm(A, X)
+    for sel in _exact_selectors(jb, np.float64):
+        got = _run_dev(jb, A, X, sel)
+        fin = np.isfinite(want)
+        assert bits_equal(got[fin], want[fin])
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+    assert np.signbit(want[0, 0]) and want[0, 0] == 0.0
+
+
+# ------------------------------------------------------------------------------------------------------
+# DMMA tensor path: tolerance contract, and a measurement of how close to the chain it is
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(16, 32, 14), (128, 128, 126), (129, 17, 127), (257, 33, 65), (256, 256, 256), (800, 900, 840), (130, 1000, 70)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_dmma_within_reference_tolerance(jb, shape):
+    M, K, N = shape
+    A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
+    want = oracle.oracle_gemm(A, X)
+    report = {}
+    for sel in _dmma_selectors(jb):
+        got = _run_dev(jb, A, X, sel)
+        assert not np.isnan(got).any()
+        ok, worst = oracle.error_bound_ok(got, want, A, X)  # 2*K*2^-52*(|A||X|)
+        assert ok, worst
+        report[jb.kernel_names()[sel - jb.EXPLICIT_BASE]] = {
+            "worst_err_over_bound": worst,
+            "bit_identical_fraction": float((got.view(np.uint64) == want.view(np.uint64)).mean()),
+        }
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f"dmma_vs_chain_{M}x{K}x{N}.json"), "w") as f:
+        json.dump(report, f, indent=1)
+
+
+def test_dmma_accumulate_and_strided(jb):
+    M, K, N = 150, 50, 66
+    A, X = randn_f((M, K), ld=151), randn_f((K, N), seed=SEED_X, ld=50)
+    D0 = randn_f((M, N), seed=5)
+    want = oracle.oracle_gemm(np.asfortranarray(A), np.asfortranarray(X), D0.copy(order="F"), accumulate=True)
+    for sel in _dmma_selectors(jb):
+        got = _run_dev(jb, A, X, sel, accumulate_into=D0)
+        assert np.abs(got - want).max() <= 2 * K * 2.0 ** -52 * (np.abs(A) @ np.abs(X) + np.abs(D0)).max()
+
+
+# ------------------------------------------------------------------------------------------------------
+# the reference-facing API: host pointers, kernel!/initkernel!/fastmul!, degenerate sizes
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_host_pointer_entry_matches_oracle(jb, dt):
+    M, K, N = 333, 129, 77
+    A, X = randn_f((M, K), dt, ld=340), randn_f((K, N), dt, SEED_X)
+    want = oracle.oracle_gemm(np.asfortranarray(A), X)
+    D = nan_f((M, N), dt, ld=400)
+    out = jb.jmul_(D, A, X, kernel=jb.F64_SIMT if dt == np.float64 else jb.F32_EXACT)
+    assert out is D and bits_equal(D, want) and np.isnan(D.base[M:, :]).all()
+    D2 = nan_f((M, N), dt)
+    jb.gemm_(D2, A, X)  # AUTO selector: tolerance contract
+    ok, worst = oracle.error_bound_ok(D2, want, np.asfortranarray(A), X)
+    assert ok, worst
+
+
+def test_host_pointer_k_panel_pipeline_is_bit_identical(jb):
+    """A > 64 MiB is staged in K panels with accumulate passes; per-element k order is unchanged."""
+    M, K, N = 4096, 2304, 512  # A = 72 MiB -> 2 panels
+    A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
+    D = nan_f((M, N))
+    jb.jmul_(D, A, X, kernel=jb.F64_SIMT)
+    assert bits_equal(D, oracle.oracle_gemm(A, X))
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_kernel_initkernel_fastmul(jb, dt):
+    Mk, Pk, N, sAD, sX = 40, 5, 23, 48, 32  # Kernel{Mk,Pk,stride_AD,stride_X,N}
+    k = jb.Kernel(Mk, Pk, sAD, sX, N)
+    rng = np.random.Generator(np.random.PCG64(3))
+    pA = rng.standard_normal(sAD * N).astype(dt)
+    pX = rng.standard_normal(sX * Pk).astype(dt)
+    pD = rng.standard_normal(sAD * Pk).astype(dt)
+    A = np.asfortranarray(pA.reshape(N, sAD).T[:Mk, :])
+    X = np.asfortranarray(pX.reshape(Pk, sX).T[:N, :])
+    D0 = np.asfortranarray(pD.reshape(Pk, sAD).T[:Mk, :])
+    pad0 = pD.reshape(Pk, sAD)[:, Mk:].copy()
+    # initkernel!: D = A*X
+    d1 = pD.copy()
+    assert jb.initkernel_(d1, pA, pX, k) is None
+    assert bits_equal(np.asfortranarray(d1.reshape(Pk, sAD).T[:Mk, :]), oracle.oracle_gemm(A, X))
+    assert bits_equal(d1.reshape(Pk, sAD)[:, Mk:], pad0)  # storage between columns untouched
+    # kernel!: D += A*X
+    d2 = pD.copy()
+    jb.kernel_(d2, pA, pX, k)
+    assert bits_equal(np.asfortranarray(d2.reshape(Pk, sAD).T[:Mk, :]), oracle.oracle_gemm(A, X, D0.copy(order="F"), accumulate=True))
+    # fastmul!: any M (the reference masks the row remainder)
+    for M in (1, 7, 13, 40):
+        Af, Xf = randn_f((M, N), dt, 11), randn_f((N, Pk), dt, 12)
+        assert bits_equal(jb.fastmul_(nan_f((M, Pk), dt), Af, Xf), oracle.oracle_gemm(Af, Xf))
+
+
+def test_degenerate_sizes(jb):
+    import torch
+
+    z = jb.jmul_(np.full((4, 3), np.nan, order="F"), np.zeros((4, 0), order="F"), np.zeros((0, 3), order="F"))
+    assert (z == 0).all()  # empty contraction: defined as zeros
+    jb.jmul_(np.zeros((0, 3), order="F"), np.zeros((0, 5), order="F"), np.zeros((5, 3), order="F"))
+    jb.jmul_(np.zeros((4, 0), order="F"), np.zeros((4, 5), order="F"), np.zeros((5, 0), order="F"))
+    dD = jb.empty_colmajor(4, 3, fill=float("nan"))
+    jb.jmul_(dD, torch.zeros((0, 4), device="cuda", dtype=torch.float64).t(), torch.zeros((3, 0), device="cuda", dtype=torch.float64).t())
+    torch.cuda.synchronize()
+    assert (dD == 0).all()
+    with pytest.raises(jb.JblasB200Error):
+        from jblas.jl_b200 import _lib
+
+        _lib.check(_lib.lib().jblas_b200_gemm_f64_dev(dD.data_ptr(), dD.data_ptr(), dD.data_ptr(), 4, 3, 3, 2, 4, 3, 0, 0, None))  # ldd < M
+
+
+# ------------------------------------------------------------------------------------------------------
+# BASELINE.json configs
+# ------------------------------------------------------------------------------------------------------
+def test_config_256_cubed_all_kernels(jb):
+    A, X = randn_f((256, 256)), randn_f((256, 256), seed=SEED_X)
+    want = oracle.oracle_gemm(A, X)
+    for sel in _exact_selectors(jb, np.float64):
+        assert bits_equal(_run_dev(jb, A, X, sel), want)
+    for sel in _dmma_selectors(jb) + [jb.F64_AUTO, jb.F64_DMMA]:
+        ok, worst = oracle.error_bound_ok(_run_dev(jb, A, X, sel), want, A, X)
+        assert ok, worst
+    assert bits_equal(_run_dev(jb, A, X, jb.F64_SIMT), want)
+
+
+def test_config_ragged_1023x777x4097(jb):
+    M, N, K = 1023, 777, 4097
+    A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
+    want = oracle.oracle_gemm(A, X)
+    assert bits_equal(_run_dev(jb, A, X, jb.F64_SIMT), want)
+    ok, worst = oracle.error_bound_ok(_run_dev(jb, A, X, jb.F64_DMMA), want, A, X)
+    assert ok, worst
+    D = nan_f((M, N))
+    jb.jmul_(D, A, X, kernel=jb.F64_SIMT)  # host-pointer entry on the ragged shape
+    assert bits_equal(D, want)
+
+
+def test_config_tall_skinny_65536x64x64(jb):
+    M, N, K = 65536, 64, 64
+    A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
+    want = oracle.oracle_gemm(A, X)
+    assert bits_equal(_run_dev(jb, A, X, jb.F64_SIMT), want)
+    ok, worst = oracle.error_bound_ok(_run_dev(jb, A, X, jb.F64_AUTO), want, A, X)
+    assert ok, worst
+
+
+def _sampled_check(jb, n, dtype_name, selector, exact, extra_rel=0.0):
+    """Full-size run on device-generated inputs; parity on a sampled sub-grid of rows x cols (each element's chain
+    is independent) plus a NaN-sentinel sweep and a checksum property over the whole result."""
+    import torch
+
+    A = jb.mrandn(n, n, dtype_name, seed=SEED_A)
+    X = jb.mrandn(n, n, dtype_name, seed=SEED_X)
+    D = jb.empty_colmajor(n, n, dtype_name, fill=float("nan"))
+    jb.jmul_(D, A, X, kernel=selector)
+    torch.cuda.synchronize()
+    assert not torch.isnan(D).any()
+    rng = np.random.Generator(np.random.PCG64(5))
+    rows = np.unique(np.concatenate([[0, 1, n - 1, n - 2, 127, 128], rng.integers(0, n, 58)]))
+    cols = np.unique(np.concatenate([[0, 1, n - 1, n - 2, 127, 128], rng.integers(0, n, 26)]))
+    tr, tc = torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()
+    As = np.asfortranarray(A[tr, :].cpu().numpy())      # the identical bits the GPU used
+    Xs = np.asfortranarray(X[:, tc].cpu().numpy())
+    got = np.asfortranarray(D[tr][:, tc].cpu().numpy())
+    want = oracle.oracle_gemm(As, Xs)
+    if exact:
+        assert bits_equal(got, want)
+    else:
+        ok, worst = oracle.error_bound_ok(got, want, As, Xs, extra_rel=extra_rel)
+        assert ok, worst
+    # size-independent property: D*1 == A*(X*1) within the reference bound scaled for the extra sum
+    ones = torch.ones(n, 1, dtype=torch.float64, device="cuda")
+    lhs = D.double() @ ones
+    rhs = A.double() @ (X.double() @ ones)
+    scale = (A.double().abs() @ (X.double().abs() @ ones))
+    eps = 2.0 ** -52 if dtype_name == "float64" else 2.0 ** -23
+    assert ((lhs - rhs).abs() <= (4 * n * eps + extra_rel) * scale).all()
+    del A, X, D
+    torch.cuda.empty_cache()
+
+
+def test_config_8192_cubed_f64_simt_sampled_bit_identical(jb):
+    _sampled_check(jb, 8192, "float64", jb.F64_SIMT, exact=True)
+
+
+def test_config_8192_cubed_f64_dmma_sampled_within_bound(jb):
+    _sampled_check(jb, 8192, "float64", jb.F64_DMMA, exact=False)
+
+
+def test_config_16384_cubed_f32_exact_sampled_bit_identical(jb):
+    _sampled_check(jb, 16384, "float32", jb.F32_EXACT, exact=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# mrandn
+# ------------------------------------------------------------------------------------------------------
+def test_mrandn_is_seeded_standard_normal(jb):
+    import torch
+
+    a = jb.mrandn(1000, 777)
+    b = jb.mrandn(1000, 777)
+    c = jb.mrandn(1000, 777, seed=SEED_X)
+    assert a.shape == (1000, 777) and a.stride() == (1, 1000) and a.dtype == torch.float64
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(a.mean().item()) < 5e-3 and abs(a.var().item() - 1.0) < 1e-2
+    assert abs((a ** 4).mean().item() - 3.0) < 0.1 and a.abs().max().item() > 4.0
+    f = jb.mrandn(1000, 777, "float32")
+    assert f.dtype == torch.float32 and torch.equal(f, a.float())  # Float64 draw rounded to Float32 (src/randmat.jl:5-10)
+    # element i depends only on (seed, i): a prefix of a longer stream is identical
+    longer = jb.mrandn(1000, 1500)
+    assert torch.equal(longer[:, :777], a)
+    odd = jb.mrandn(3, 5)
+    assert torch.isfinite(odd).all()
