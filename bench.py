@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the jmul! path on B200 (contract: see the task brief, section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c4a|c4b|c5] [--kernel auto|dmma|simt]
+
+One "step" = one product D = A*X over one batch of synthetic N(0,1) input (mrandn, src/randmat.jl:5-14).
+  N = 1  : BASELINE.json configs[1]  -- Float64 M=N=K=8192 (the config the metric is quoted on).
+  N > 1  : the column-sharded mode: every rank owns an 8192-column block of X and D, A (8192x8192)
+           lives on rank 0 and is broadcast in K panels overlapped with the local GEMM -> weak scaling,
+           N = 1 being exactly configs[1].  `--workload c5` runs BASELINE configs[4] instead (32768^3 strong).
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference's own loop nest
+(oracle/jmul_baseline.c; Julia is not available) on rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED_A = 0x6A424C41
+SEED_X = SEED_A + 1
+METRIC = "GEMM TFLOP/s (FP64, FP32) and % of roofline at 1/2/4/8 B200 vs CPU jBLAS"
+FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
+FP32_NOMINAL_TFLOPS = 74.4
+
+WORKLOADS = {
+    # name: (dtype, M, N, K, description)
+    "c2": ("float64", 8192, 8192, 8192, "Float64 jmul! M=N=K=8192 (BASELINE configs[1])"),
+    "c3": ("float32", 16384, 16384, 16384, "Float32 jmul! M=N=K=16384 exact SIMT (BASELINE configs[2])"),
+    "c4a": ("float64", 1023, 777, 4097, "Float64 jmul! ragged M=1023 N=777 K=4097 (BASELINE configs[3])"),
+    "c4b": ("float64", 65536, 64, 64, "Float64 jmul! tall-skinny M=65536 N=64 K=64 (BASELINE configs[3])"),
+    "c5": ("float64", 32768, 32768, 32768, "Float64 jmul! M=N=K=32768 column-sharded (BASELINE configs[4])"),
+}
+
+
+# --------------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region
+# --------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY place bench.py touches oracle/: as the reported baseline, never as the product)
+# --------------------------------------------------------------------------------------------------------
+class CpuSlab:
+    """The reference's jmul! loop nest (restatement, oracle/jmul_baseline.c) on a bounded slab of column tiles."""
+
+    def __init__(self, dtype: str, M: int, N: int, K: int, target_s: float, nthreads: int = 1):
+        import numpy as np
+
+        import oracle
+
+        self.oracle, self.np = oracle, np
+        self.dtype, self.M, self.N, self.K, self.nthreads = dtype, M, N, K, nthreads
+        dt = np.float64 if dtype == "float64" else np.float32
+        self.vl, self.rows, self.cols = oracle.jmul_baseline_tile(np.dtype(dt).itemsize)
+        rng = np.random.Generator(np.random.PCG64(SEED_A))
+        self.max_tiles = max(1, N // self.cols)
+        self.A = np.asfortranarray(rng.standard_normal((K, M)).T.astype(dt))
+        probe_tiles = min(self.max_tiles, 4)
+        Xp = np.asfortranarray(rng.standard_normal((probe_tiles * self.cols, K)).T.astype(dt))
+        Dp = np.empty((M, probe_tiles * self.cols), dtype=dt, order="F")
+        t = time.perf_counter()
+        oracle.jmul_baseline(Dp, self.A, Xp, nthreads=nthreads)
+        per_tile = (time.perf_counter() - t) / probe_tiles
+        self.tiles = int(min(self.max_tiles, max(probe_tiles, target_s / max(per_tile, 1e-9))))
+        self.X = np.asfortranarray(rng.standard_normal((self.tiles * self.cols, K)).T.astype(dt))
+        self.D = np.empty((M, self.tiles * self.cols), dtype=dt, order="F")
+
+    def run(self):
+        t = time.perf_counter()
+        r, c = self.oracle.jmul_baseline(self.D, self.A, self.X, nthreads=self.nthreads)
+        sec = time.perf_counter() - t
+        flops = 2.0 * r * c * self.K  # only what the reference's tile loops cover (it skips remainder rows/cols)
+        return flops, sec, (r, c)
+
+    def describe(self, r, c, sec):
+        return (f"restatement of the jmul! loop nest (Julia unavailable): tile {self.rows}x{self.cols} from pick_kernel_size, {self.tiles} of "
+                f"{self.max_tiles} column tiles of the {self.M}x{self.N}x{self.K} {self.dtype} workload = {r}x{c} outputs in {sec:.1f} s, "
+                f"{self.nthreads} thread (the reference is single-threaded); host has {os.cpu_count()} cores")
+
+
+def cpu_baseline_sample(dtype: str, M: int, N: int, K: int, target_s: float = 12.0, nthreads: int = 1):
+    slab = CpuSlab(dtype, M, N, K, target_s, nthreads)
+    flops, sec, (r, c) = slab.run()
+    return {"value": flops / sec / 1e12, "unit": "TFLOP/s", "cores": nthreads, "kind": "port", "sample": slab.describe(r, c, sec)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    dtype, M, N, K, desc = WORKLOADS[args.workload or "c2"]
+    slab = CpuSlab(dtype, M, N, K, target_s=4.0)
+    for _ in range(args.warmup):
+        slab.run()
+    tot_flops = tot_s = 0.0
+    r = c = 0
+    for _ in range(args.steps):
+        f, s_, (r, c) = slab.run()
+        tot_flops += f
+        tot_s += s_
+    value = tot_flops / tot_s / 1e12
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic N(0,1) (mrandn), host PCG64",
+        "config": {"workload": desc, "note": "each step = a bounded slab of column tiles of this workload on 1 host core (the reference is single-threaded)"},
+        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": 1, "kind": "port", "sample": slab.describe(r, c, tot_s / max(args.steps, 1))},
+        "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:  # convenience: relaunch ourselves under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                   "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+            return subprocess.call(cmd)
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from jblas.jl_b200 import build
+
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    import jblas.jl_b200 as jb
+    from jblas.jl_b200 import _lib
+    from jblas.jl_b200.multigpu import ShardedGemm
+
+    jb.init(local_rank)
+    wl = args.workload or "c2"
+    dtype, M, N, K, desc = WORKLOADS[wl]
+    if world > 1 and wl == "c2":
+        n_total, scaling = N * world, "weak"     # every rank owns an 8192-column block
+        desc = f"Float64 jmul! column-sharded: M=K=8192, N=8192 per GPU x {world} GPUs, A broadcast from rank 0 in K panels"
+    else:
+        n_total, scaling = N, ("strong" if world > 1 else "weak")
+    selector = {"auto": None, "dmma": jb.F64_DMMA, "simt": jb.F64_SIMT}[args.kernel]
+    if dtype == "float32":
+        selector = None
+    sg = ShardedGemm(M, K, n_total, panel_k=args.panel_k, kernel=selector)
+    A = jb.mrandn(M, K, dtype, seed=SEED_A) if rank == 0 else jb.empty_colmajor(M, K, dtype)
+    X = jb.mrandn(K, sg.shard_cols, dtype, seed=SEED_X, first_col=sg.c0)
+    D = jb.empty_colmajor(M, sg.shard_cols, dtype, fill=float("nan"))
+    es = 8 if dtype == "float64" else 4
+    flops_step = 2.0 * M * K * n_total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sg(D, A, X)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    launches0 = jb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        sg(D, A, X)
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = jb.launch_count() - launches0
+    total_ms = float(ms.item())
+    value = flops_step * args.steps / (total_ms * 1e-3) / 1e12
+    clocks = sampler.summary(t0, t1) if rank == 0 else None
+    if rank == 0:
+        sampler.stop()
+    assert not torch.isnan(D).any().item(), "NaN sentinel survived: some element of D was not written"
+
+    # ---- roofline of the dominant kernel (the GEMM kernel itself: at N=1 the step IS one launch) ----
+    roofline = None
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        if dtype == "float64":
+            dfma, _ = jb.probe_pipe("dfma", 40000)
+            dmma, _ = jb.probe_pipe("dmma", 4000)
+            peak, nominal = max(dfma, dmma), FP64_NOMINAL_TFLOPS
+            probe = {"dfma_tflops": dfma, "dmma_tflops": dmma}
+        else:
+            ffma, _ = jb.probe_pipe("ffma", 40000)
+            peak, nominal = ffma, FP32_NOMINAL_TFLOPS
+            probe = {"ffma_tflops": ffma}
+        per_launch_flops = flops_step / world / sg.launches_per_call()
+        # kernel-only duration: time the local kernel launches alone on this stream (no collective)
+        k0, k1 = sg.panels[0]
+        ke0, ke1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(args.steps, 10))
+        from jblas.jl_b200 import api
+        api._gemm(D, A[:, k0:k1], X[k0:k1, :], False, selector)
+        torch.cuda.synchronize()
+        ke0.record()
+        for _ in range(reps):
+            api._gemm(D, A[:, k0:k1], X[k0:k1, :], False, selector)
+        ke1.record()
+        torch.cuda.synchronize()
+        kms = ke0.elapsed_time(ke1) / reps
+        achieved = per_launch_flops / (kms * 1e-3) / 1e12
+        algo_bytes = (M * (k1 - k0) + (k1 - k0) * sg.shard_cols + M * sg.shard_cols) * es
+        pl = jb.plan(M, k1 - k0, sg.shard_cols, dtype, kernel=selector)
+        roofline = {
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "kernel": pl["kernel"], "kernel_ms": kms, "flops_per_launch": per_launch_flops, "algorithmic_bytes_per_launch": algo_bytes,
+            "peak_source": ("live register-only pipe probe in this run (MEASURED_PEAKS.json carries only HBM and bf16 figures): " + json.dumps(probe)),
+            "frac_of_nominal": achieved / nominal, "nominal_peak": nominal,
+            "hbm_gbs_if_bytes_bound": algo_bytes / (kms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_src,
+        }
+
+    # ---- e2e: the reference-facing call with HOST buffers (H2D of A and X, D2H of D inside the timed region) ----
+    e2e = run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_step, selector)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(dtype, M, N, K, target_s=12.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic N(0,1), device-generated Philox (mrandn analogue), seeds jBLA/jBLA+1",
+            "config": {"workload": desc, "M": M, "K": K, "N_total": n_total, "N_per_gpu": sg.shard_cols, "kernel_selector": args.kernel,
+                       "parallelism": f"column-shard x{world}" + (f", A broadcast in {len(sg.panels)} K-panels of {args.panel_k}" if world > 1 else ""),
+                       "l2": f"inputs larger than L2: A+X+D = {(M * K + K * sg.shard_cols + M * sg.shard_cols) * es / 2**20:.0f} MiB per GPU vs 126 MB L2"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_step, selector):
+    """Same metric through the public host-facing API: every step copies that step's inputs host->device from
+    pinned host memory and reads the result back."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    es = 8 if dtype == "float64" else 4
+    steps = max(1, min(args.steps, 5))
+    L = _lib.lib()
+    h2d = d2h = 0
+    if world == 1:
+        # the C-ABI host-pointer entry (what a Julia ccall hits); caller buffers pinned once with jblas_b200_host_register
+        Ah = np.asfortranarray(A.cpu().numpy())
+        Xh = np.asfortranarray(X.cpu().numpy())
+        Dh = np.full((M, sg.shard_cols), np.nan, dtype=Ah.dtype, order="F")
+        for a in (Ah, Xh, Dh):
+            _lib.check(L.jblas_b200_host_register(a.ctypes.data, a.nbytes))
+        try:
+            jb.jmul_(Dh, Ah, Xh, kernel=selector)  # warm-up (workspace allocation)
+            t = time.perf_counter()
+            for _ in range(steps):
+                jb.jmul_(Dh, Ah, Xh, kernel=selector)
+            sec = time.perf_counter() - t
+        finally:
+            for a in (Ah, Xh, Dh):
+                L.jblas_b200_host_unregister(a.ctypes.data)
+        assert not np.isnan(Dh).any()
+        h2d, d2h = Ah.nbytes + Xh.nbytes, Dh.nbytes
+        return {"value": flops_step * steps / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": steps, "ms_per_step": 1e3 * sec / steps, "api": "jblas_b200_gemm_f64 (host pointers, pinned by jblas_b200_host_register)"}
+    # N > 1: pinned host shards; root uploads A, every rank uploads its X block and downloads its D block
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    Xh = torch.empty((sg.shard_cols, K), dtype=tdt).pin_memory(); Xh.copy_(X.t())
+    Dh = torch.empty((sg.shard_cols, M), dtype=tdt).pin_memory()
+    Ah = None
+    if rank == 0:
+        Ah = torch.empty((K, M), dtype=tdt).pin_memory(); Ah.copy_(A.t())
+
+    def step():
+        if rank == 0:
+            A.t().copy_(Ah, non_blocking=True)
+        X.t().copy_(Xh, non_blocking=True)
+        sg(D, A, X)
+        Dh.copy_(D.t(), non_blocking=True)
+
+    step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.barrier()
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    h2d = (M * K * es if rank == 0 else 0) + K * sg.shard_cols * es
+    tot = torch.tensor([float(h2d), float(M * sg.shard_cols * es)], device=dev, dtype=torch.float64)
+    dist.all_reduce(tot)
+    return {"value": flops_step * steps / (ms.item() * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tot[0].item()),
+            "d2h_bytes_per_step": int(tot[1].item()), "steps": steps, "ms_per_step": ms.item() / steps,
+            "api": "ShardedGemm on pinned host shards (H2D of A on rank 0 + X shard per rank, D2H of D shard per rank)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="auto", choices=["auto", "dmma", "simt"])
+    ap.add_argument("--panel-k", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

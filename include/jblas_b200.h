@@ -96,7 +96,7 @@ int jblas_b200_initkernel_f32(float* pD, const float* pA, const float* pX, int64
                               int64_t stride_X, int64_t N);
 
 /* ---- the hot path on DEVICE pointers (matrices resident in HBM) -----------------------------------
- * Same contract, asynchronous on `stream` (a cudaStream_t; NULL = the context's stream).  These are what
+ * Same contract, asynchronous on `stream` (a cudaStream_t; NULL = the CUDA default stream).  These are what
  * the multi-GPU driver and the benchmarks call; D, A, X must not alias. */
 int jblas_b200_gemm_f64_dev(double* D, const double* A, const double* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
                             int64_t lda, int64_t ldx, int accumulate, int kernel, void* stream);

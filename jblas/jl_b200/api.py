@@ -236,12 +236,14 @@ def plan(M: int, K: int, N: int, dtype="float64", kernel: int | None = None, ldd
     out = (ctypes.c_int64 * 10)()
     L = _lib.lib()
     check(L.jblas_b200_plan(dt, M, K, N, ldd or M, lda or M, ldx or K, kernel, out))
+    name = L.jblas_b200_kernel_name(int(out[0])).decode()
+    staging = "TMA cp.async.bulk.tensor, 128B swizzle" if "tma" in name else ("cp.async 16B" if out[9] else "cp.async element-wise")
     return {
-        "kernel": L.jblas_b200_kernel_name(int(out[0])).decode(),
+        "kernel": name,
         "kernel_index": int(out[0]),
         "tile_m": int(out[1]), "tile_n": int(out[2]), "tile_k": int(out[3]),
         "stages": int(out[4]), "threads": int(out[5]), "grid": int(out[6]), "raster_group": int(out[7]),
-        "smem_bytes": int(out[8]), "staging": "cp.async 16B" if out[9] else "cp.async element-wise",
+        "smem_bytes": int(out[8]), "staging": staging,
     }
 
 

@@ -15,6 +15,7 @@
 
 #include "aux_kernels.cuh"
 #include "gemm_dmma.cuh"
+#include "gemm_dmma_tma.cuh"
 #include "gemm_simt.cuh"
 
 using namespace jb;
@@ -68,25 +69,29 @@ static int require_init()
 // ---------------------------------------------------------------------------------------------------------
 enum Family { FAM_SIMT = 0, FAM_DMMA = 1 };
 
+typedef int (*LaunchFn)(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                        int tiles_m, int tiles_n, int group_m, cudaStream_t s);
+
 struct KernelInfo {
     const char* name;
     int dtype;   // JBLAS_B200_DT_*
     int family;  // Family
     int bm, bn, bk, stages, threads;
     size_t smem;
-    float eff;  // relative per-tile efficiency used by the planner (1.0 = the big tile)
-    // launchers indexed [aligned][acc]
-    void (*launch[2][2])(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda,
-                         int64_t ldx, int tiles_m, int tiles_n, int group_m, cudaStream_t s);
+    float eff;           // relative per-tile efficiency used by the planner (1.0 = the plain 128x128 tile)
+    bool needs_aligned;  // TMA kernels: 16-byte aligned bases and leading dimensions only
+    bool persistent;     // grid = min(tiles, #SMs), CTAs loop over the rasterised tile list
+    LaunchFn launch[2][2];  // [aligned][acc]
     cudaError_t (*set_attr)();
 };
 
 template <typename T, typename Cfg, bool ALIGNED, bool ACC>
-static void launch_simt(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
-                        int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+static int launch_simt(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                       int tiles_m, int tiles_n, int group_m, cudaStream_t s)
 {
     gemm_simt_kernel<T, Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
         (T*)D, (const T*)A, (const T*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m);
+    return 0;
 }
 template <typename T, typename Cfg>
 static cudaError_t attr_simt()
@@ -101,11 +106,12 @@ static cudaError_t attr_simt()
     return cudaSuccess;
 }
 template <typename Cfg, bool ALIGNED, bool ACC>
-static void launch_dmma(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
-                        int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+static int launch_dmma(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                       int tiles_m, int tiles_n, int group_m, cudaStream_t s)
 {
     gemm_dmma_kernel<Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
         (double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m);
+    return 0;
 }
 template <typename Cfg>
 static cudaError_t attr_dmma()
@@ -120,9 +126,69 @@ static cudaError_t attr_dmma()
     return cudaSuccess;
 }
 
+// ---- TMA tensor maps (driver entry point resolved at run time: the library must load without libcuda.so.1) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+
+static int get_encode_tiled()
+{
+    if (g_encode_tiled) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(JBLAS_B200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver (%s)", cudaGetErrorString(e));
+    g_encode_tiled = (EncodeTiledFn)fn;
+    return 0;
+}
+
+// 2-D column-major operand: dim0 = rows (contiguous), dim1 = cols (stride ld elements); box = box_r x box_c, 128B swizzle
+static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esize, uint64_t rows, uint64_t cols,
+                        uint64_t ld, uint32_t box_r, uint32_t box_c)
+{
+    if (int rc = get_encode_tiled()) return rc;
+    cuuint64_t gdim[2] = {rows, cols};
+    cuuint64_t gstride[1] = {ld * (uint64_t)esize};
+    cuuint32_t box[2] = {box_r, box_c};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(JBLAS_B200_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+template <typename Cfg, bool ACC>
+static int launch_dmma_tma(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                           int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+{
+    CUtensorMap mapA, mapX;
+    if (int rc = make_tmap_2d(&mapA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 16, 16)) return rc;
+    if (int rc = make_tmap_2d(&mapX, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, (uint64_t)K, (uint64_t)N, (uint64_t)ldx, 16, Cfg::BN)) return rc;
+    int grid = tiles_m * tiles_n;
+    if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
+    gemm_dmma_tma_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mapA, mapX, (double*)D, M, N, K, ldd, tiles_m, tiles_n,
+                                                                           group_m);
+    return 0;
+}
+static int launch_needs_alignment(void*, const void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, int, int,
+                                  cudaStream_t)
+{
+    return fail(JBLAS_B200_EUNSUPPORTED, "this kernel needs 16-byte aligned A/X bases and even leading dimensions (TMA)");
+}
+template <typename Cfg>
+static cudaError_t attr_dmma_tma()
+{
+    cudaError_t e = cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+}
+
 #define SIMT_ENTRY(NAME, T, DT, CFG, EFF)                                                                          \
     {                                                                                                              \
-        NAME, DT, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,                  \
+        NAME, DT, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF, false, false,    \
             {{launch_simt<T, CFG, false, false>, launch_simt<T, CFG, false, true>},                                \
              {launch_simt<T, CFG, true, false>, launch_simt<T, CFG, true, true>}},                                 \
             attr_simt<T, CFG>                                                                                      \
@@ -130,9 +196,17 @@ static cudaError_t attr_dmma()
 #define DMMA_ENTRY(NAME, CFG, EFF)                                                                                 \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F64, FAM_DMMA, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
+            false, false,                                                                                          \
             {{launch_dmma<CFG, false, false>, launch_dmma<CFG, false, true>},                                      \
              {launch_dmma<CFG, true, false>, launch_dmma<CFG, true, true>}},                                       \
             attr_dmma<CFG>                                                                                         \
+    }
+#define DMMA_TMA_ENTRY(NAME, CFG, EFF)                                                                             \
+    {                                                                                                              \
+        NAME, JBLAS_B200_DT_F64, FAM_DMMA, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
+            true, true,                                                                                            \
+            {{launch_needs_alignment, launch_needs_alignment}, {launch_dmma_tma<CFG, false>, launch_dmma_tma<CFG, true>}}, \
+            attr_dmma_tma<CFG>                                                                                     \
     }
 
 //                         T      WM WN BK ST MINB
@@ -145,7 +219,10 @@ using S32_64x64 = SimtCfg<float, 1, 2, 16, 4, 4>;
 using D64_128x128 = DmmaCfg<2, 4, 16, 4>;
 using D64_128x64 = DmmaCfg<2, 2, 16, 4>;
 using D64_64x64 = DmmaCfg<1, 2, 16, 4>;
+using T64_k16s6 = DmmaTmaCfg<1, 6>;  // 6 stages of 32 KiB
+using T64_k32s3 = DmmaTmaCfg<2, 3>;  // 3 stages of 64 KiB
 
+// NOTE: indices are part of the tuning interface (selector 100+i); append, do not reorder.
 static const KernelInfo g_kernels[] = {
     /* 0 */ SIMT_ENTRY("simt_f64_128x128x16", double, JBLAS_B200_DT_F64, S64_128x128, 1.00f),
     /* 1 */ SIMT_ENTRY("simt_f64_128x64x16", double, JBLAS_B200_DT_F64, S64_128x64, 0.95f),
@@ -156,6 +233,8 @@ static const KernelInfo g_kernels[] = {
     /* 6 */ SIMT_ENTRY("simt_f32_128x128x16", float, JBLAS_B200_DT_F32, S32_128x128, 1.00f),
     /* 7 */ SIMT_ENTRY("simt_f32_128x64x16", float, JBLAS_B200_DT_F32, S32_128x64, 0.95f),
     /* 8 */ SIMT_ENTRY("simt_f32_64x64x16", float, JBLAS_B200_DT_F32, S32_64x64, 0.85f),
+    /* 9 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x16_s6", T64_k16s6, 1.10f),
+    /* 10 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x32_s3", T64_k32s3, 1.08f),
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
@@ -193,11 +272,14 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
             return fail(JBLAS_B200_EUNSUPPORTED, "3xTF32 tcgen05 path is not built in this version");
         else return fail(JBLAS_B200_EINVAL, "unknown Float32 mode selector %d", selector);
     }
+    const int vec = dtype == JBLAS_B200_DT_F64 ? 2 : 4;
+    out->aligned = is_aligned16(A) && is_aligned16(X) && (lda % vec == 0) && (ldx % vec == 0);
     int best = -1;
     double best_t = 0;
     for (int i = 0; i < NUM_KERNELS; ++i) {
         const KernelInfo& k = g_kernels[i];
         if (explicit_idx >= 0 ? (i != explicit_idx) : (k.dtype != dtype || k.family != family)) continue;
+        if (explicit_idx < 0 && k.needs_aligned && !out->aligned) continue;
         int64_t tiles = ((M + k.bm - 1) / k.bm) * ((N + k.bn - 1) / k.bn);
         double per_tile = (double)k.bm * k.bn;
         double waves = (double)((tiles + num_sms - 1) / num_sms);
@@ -216,8 +298,6 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
     // raster group: keep ~sqrt(#SMs) tile rows together so a resident wave touches a near-square block
     out->group_m = out->tiles_m < 12 ? out->tiles_m : 12;
     if (out->group_m < 1) out->group_m = 1;
-    const int vec = dtype == JBLAS_B200_DT_F64 ? 2 : 4;
-    out->aligned = is_aligned16(A) && is_aligned16(X) && (lda % vec == 0) && (ldx % vec == 0);
     return 0;
 }
 
@@ -261,7 +341,7 @@ static int gemm_dev(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t 
     if (int rc = require_init()) return rc;
     if (int rc = validate(D, A, X, M, K, N, ldd, lda, ldx)) return rc;
     if (M == 0 || N == 0) return 0;
-    if (!s) s = g_ctx.stream;
+    // s == NULL is the CUDA default stream, exactly as for any CUDA API: the caller's stream ordering is kept
     if (K == 0) {  // empty contraction: jmul! would read X[1,j] out of bounds; defined here as D = 0 (or D unchanged)
         if (!accumulate) {
             zero_fill_kernel<T><<<g_ctx.num_sms * 4, 256, 0, s>>>(D, M, N, ldd);
@@ -274,8 +354,9 @@ static int gemm_dev(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t 
     if (int rc = make_plan(dtype, M, K, N, lda, ldx, A, X, selector, &p)) return rc;
     if (int rc = set_all_attrs()) return rc;
     const KernelInfo& k = g_kernels[p.kidx];
-    k.launch[p.aligned ? 1 : 0][accumulate ? 1 : 0](D, A, X, (int)M, (int)N, (int)K, ldd, lda, ldx, p.tiles_m, p.tiles_n,
-                                                    p.group_m, s);
+    if (int rc = k.launch[p.aligned ? 1 : 0][accumulate ? 1 : 0](D, A, X, (int)M, (int)N, (int)K, ldd, lda, ldx, p.tiles_m,
+                                                                 p.tiles_n, p.group_m, s))
+        return rc;
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -538,7 +619,7 @@ int jblas_b200_host_unregister(void* host)
 int jblas_b200_stream_sync(void* stream)
 {
     if (int rc = require_init()) return rc;
-    CUDA_TRY(cudaStreamSynchronize(stream ? (cudaStream_t)stream : g_ctx.stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
 
@@ -547,7 +628,7 @@ int jblas_b200_randn_fill(void* dptr, int64_t first, int64_t n, uint64_t seed, i
     if (int rc = require_init()) return rc;
     if (n < 0 || first < 0 || (n > 0 && !dptr)) return fail(JBLAS_B200_EINVAL, "bad randn_fill arguments");
     if (n == 0) return 0;
-    cudaStream_t s = stream ? (cudaStream_t)stream : g_ctx.stream;
+    cudaStream_t s = (cudaStream_t)stream;  // NULL = the CUDA default stream
     int blocks = g_ctx.num_sms * 8;
     if (dtype == JBLAS_B200_DT_F64)
         randn_fill_kernel<double><<<blocks, 256, 0, s>>>((double*)dptr, first, n, seed);
@@ -571,7 +652,9 @@ int jblas_b200_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t ldd, int
     if (int rc = make_plan(dtype, M, K, N, lda, ldx, nullptr, nullptr, selector, &p)) return rc;
     const KernelInfo& k = g_kernels[p.kidx];
     out[0] = p.kidx; out[1] = k.bm; out[2] = k.bn; out[3] = k.bk; out[4] = k.stages; out[5] = k.threads;
-    out[6] = (int64_t)p.tiles_m * p.tiles_n; out[7] = p.group_m; out[8] = (int64_t)k.smem; out[9] = p.aligned ? 1 : 0;
+    out[6] = (int64_t)p.tiles_m * p.tiles_n;
+    if (k.persistent && out[6] > (g_ctx.num_sms > 0 ? g_ctx.num_sms : 148)) out[6] = g_ctx.num_sms > 0 ? g_ctx.num_sms : 148;
+    out[7] = p.group_m; out[8] = (int64_t)k.smem; out[9] = p.aligned ? 1 : 0;
     return 0;
 }
 const char* jblas_b200_kernel_name(int kidx) { return (kidx >= 0 && kidx < NUM_KERNELS) ? g_kernels[kidx].name : ""; }
@@ -589,7 +672,9 @@ int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms_out)
     CUDA_TRY(cudaMalloc(&out, 256));
     const int blocks = g_ctx.num_sms * 4, threads = 256;
     double flops = 0;
-    for (int rep = 0; rep < 2; ++rep) {  // rep 0 = warm-up
+    // 3 warm-up launches (clocks ramp from idle over tens of ms), then the best of 5 timed launches
+    float best_ms = 0.f;
+    for (int rep = 0; rep < 8; ++rep) {
         CUDA_TRY(cudaEventRecord(g_ctx.ev0, s));
         if (kind == 0) {
             probe_dfma_kernel<16><<<blocks, threads, 0, s>>>((double*)out, iters, 1.0000001, 1e-9);
@@ -607,9 +692,11 @@ int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms_out)
         g_launches++;
         CUDA_TRY(cudaEventRecord(g_ctx.ev1, s));
         CUDA_TRY(cudaStreamSynchronize(s));
+        float rep_ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&rep_ms, g_ctx.ev0, g_ctx.ev1));
+        if (rep >= 3 && (best_ms == 0.f || rep_ms < best_ms)) best_ms = rep_ms;
     }
-    float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_ctx.ev0, g_ctx.ev1));
+    float ms = best_ms;
     CUDA_TRY(cudaFree(out));
     *tflops = flops / (ms * 1e-3) / 1e12;
     if (ms_out) *ms_out = ms;

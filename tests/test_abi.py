@@ -50,9 +50,11 @@ def test_header_cites_reference_lines():
 
 def test_planner_is_pure_host_logic(jb):
     p = jb.plan(8192, 8192, 8192)
-    assert p["tile_m"] == 128 and p["tile_n"] == 128 and p["grid"] == 64 * 64 and p["staging"] == "cp.async 16B"
-    assert jb.plan(8192, 8192, 8192, kernel=jb.F64_SIMT)["kernel"].startswith("simt_f64")
-    assert jb.plan(8192, 8192, 8192, kernel=jb.F64_DMMA)["kernel"].startswith("dmma_f64")
+    # AUTO on an aligned big square: the persistent TMA warp-specialised DMMA kernel, one CTA per SM
+    assert p["kernel"].startswith("dmma_tma_f64") and p["tile_m"] == 128 and p["tile_n"] == 128 and p["grid"] == 148
+    s = jb.plan(8192, 8192, 8192, kernel=jb.F64_SIMT)
+    assert s["kernel"].startswith("simt_f64") and s["grid"] == 64 * 64 and s["staging"] == "cp.async 16B"
+    assert jb.plan(8192, 8192, 8192, kernel=jb.F64_DMMA)["kernel"].startswith("dmma")
     # ragged leading dimensions (M = 1023 doubles per column) cannot use 16-byte staging
     r = jb.plan(1023, 4097, 777)
     assert r["staging"] == "cp.async element-wise" and r["grid"] >= 56

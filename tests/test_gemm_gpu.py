@@ -27,8 +27,10 @@ def _exact_selectors(jb, dt):
     return [jb.EXPLICIT_BASE + i for i, n in enumerate(names) if n.startswith(tag)]
 
 
-def _dmma_selectors(jb):
-    return [jb.EXPLICIT_BASE + i for i, n in enumerate(jb.kernel_names()) if n.startswith("dmma_f64")]
+def _dmma_selectors(jb, tma=True):
+    """cp.async DMMA kernels and (tma=True) the TMA warp-specialised ones (those need 16-byte aligned operands)."""
+    return [jb.EXPLICIT_BASE + i for i, n in enumerate(jb.kernel_names())
+            if n.startswith("dmma_f64") or (tma and n.startswith("dmma_tma_f64"))]
 
 
 def _run_dev(jb, A, X, kernel, accumulate_into=None, ldd=None):
@@ -106,9 +108,8 @@ def test_exact_kernels_strided_leading_dimensions(jb, lds, dt):
         jb.jmul_(dD, dA, dX, kernel=sel)
         torch.cuda.synchronize()
         assert bits_equal(to_host(dD), want)
-        parent = dD.t().untyped_storage()  # the padding rows M..ldd-1 of every column must be untouched
-        full = torch.empty(0, dtype=dD.dtype, device=dD.device).set_(parent).view(N, ldd).cpu().numpy()
-        assert np.isnan(full[:, M:]).all()
+        full = dD._base.cpu().numpy()  # the (N, ldd) storage: padding rows M..ldd-1 of every column must be untouched
+        assert full.shape == (N, ldd) and np.isnan(full[:, M:]).all()
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
@@ -158,6 +159,11 @@ def test_dmma_within_reference_tolerance(jb, shape):
     want = oracle.oracle_gemm(A, X)
     report = {}
     for sel in _dmma_selectors(jb):
+        name = jb.kernel_names()[sel - jb.EXPLICIT_BASE]
+        if "tma" in name and (M % 2 or K % 2):  # TMA needs 16-byte aligned leading dimensions; AUTO never picks it here
+            with pytest.raises(jb.JblasB200Error):
+                _run_dev(jb, A, X, sel)
+            continue
         got = _run_dev(jb, A, X, sel)
         assert not np.isnan(got).any()
         ok, worst = oracle.error_bound_ok(got, want, A, X)  # 2*K*2^-52*(|A||X|)
@@ -176,9 +182,30 @@ def test_dmma_accumulate_and_strided(jb):
     A, X = randn_f((M, K), ld=151), randn_f((K, N), seed=SEED_X, ld=50)
     D0 = randn_f((M, N), seed=5)
     want = oracle.oracle_gemm(np.asfortranarray(A), np.asfortranarray(X), D0.copy(order="F"), accumulate=True)
-    for sel in _dmma_selectors(jb):
+    for sel in _dmma_selectors(jb, tma=False):
         got = _run_dev(jb, A, X, sel, accumulate_into=D0)
         assert np.abs(got - want).max() <= 2 * K * 2.0 ** -52 * (np.abs(A) @ np.abs(X) + np.abs(D0)).max()
+
+
+@pytest.mark.parametrize("shape", [(150, 50, 66), (128, 16, 128), (1, 2, 1), (300, 1000, 260), (129, 36, 255)], ids=str)
+def test_dmma_tma_kernels_even_strides_accumulate_edges(jb, shape):
+    """The TMA warp-specialised kernels: ragged M/N/K (zero-filled boxes), ld > rows (even), accumulate."""
+    M, K, N = shape
+    lda, ldx, ldd = M + (M % 2) + 2, K + (K % 2) + 4, M + 3
+    A, X = randn_f((M, K), ld=lda), randn_f((K, N), seed=SEED_X, ld=ldx)
+    Ad, Xd = np.asfortranarray(A), np.asfortranarray(X)
+    want = oracle.oracle_gemm(Ad, Xd)
+    D0 = randn_f((M, N), seed=5)
+    want_acc = oracle.oracle_gemm(Ad, Xd, D0.copy(order="F"), accumulate=True)
+    tma = [s for s in _dmma_selectors(jb) if "tma" in jb.kernel_names()[s - jb.EXPLICIT_BASE]]
+    assert tma
+    for sel in tma:
+        got = _run_dev(jb, A, X, sel, ldd=ldd)
+        assert not np.isnan(got).any()
+        ok, worst = oracle.error_bound_ok(got, want, Ad, Xd)
+        assert ok, worst
+        got = _run_dev(jb, A, X, sel, accumulate_into=D0)
+        assert np.abs(got - want_acc).max() <= 2 * K * 2.0 ** -52 * (np.abs(Ad) @ np.abs(Xd) + np.abs(D0)).max()
 
 
 # ------------------------------------------------------------------------------------------------------

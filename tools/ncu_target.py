@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""Tiny launcher for ncu captures: run `reps` launches of one kernel selector on one shape.
+    python tools/ncu_target.py float64 8192 8192 8192 <selector|auto|dmma|simt> [reps]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import jblas.jl_b200 as jb  # noqa: E402
+from jblas.jl_b200 import api  # noqa: E402
+
+dtype, M, N, K, sel = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
+reps = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+sel = {"auto": None, "dmma": jb.F64_DMMA, "simt": jb.F64_SIMT}.get(sel, None) if not sel.isdigit() else int(sel)
+jb.init(0)
+A = jb.mrandn(M, K, dtype, seed=1)
+X = jb.mrandn(K, N, dtype, seed=2)
+D = jb.empty_colmajor(M, N, dtype)
+for _ in range(reps):
+    api._gemm(D, A, X, False, sel)
+torch.cuda.synchronize()
+print("done", jb.plan(M, K, N, dtype, kernel=sel)["kernel"])
