@@ -134,7 +134,9 @@ int64_t jblas_b200_launch_count(void);
 float jblas_b200_time_last_ms(void);
 
 /* ---- pipe-rate probes (roofline denominators; registers only, no memory traffic) --------------------
- * kind: 0 = DFMA, 1 = DMMA m8n8k4, 2 = FFMA.  Returns achieved TFLOP/s (2 flop per FMA) in *tflops. */
+ * kind: 0 = DFMA, 1 = DMMA m8n8k4, 2 = FFMA (independent chains, operands reused);
+ *       3 = DMMA, 4 = DFMA, 5 = FFMA, 6 = FFMA2 in the GEMM micro-kernel operand pattern (8x8 outer product).
+ * Returns achieved TFLOP/s (2 flop per FMA) in *tflops. */
 int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms);
 
 #ifdef __cplusplus

@@ -260,5 +260,5 @@ def probe_pipe(kind: str, iters: int = 20000):
     """Measured pipe rate in TFLOP/s for 'dfma' | 'dmma' | 'ffma' (register-only loop)."""
     init()
     tf, ms = ctypes.c_double(), ctypes.c_float()
-    check(_lib.lib().jblas_b200_probe_pipe({"dfma": 0, "dmma": 1, "ffma": 2}[kind], iters, ctypes.byref(tf), ctypes.byref(ms)))
+    check(_lib.lib().jblas_b200_probe_pipe({"dfma": 0, "dmma": 1, "ffma": 2, "dmma_tile": 3, "dfma_tile": 4, "ffma_tile": 5, "ffma2_tile": 6}[kind], iters, ctypes.byref(tf), ctypes.byref(ms)))
     return tf.value, ms.value

@@ -104,4 +104,92 @@ __global__ void __launch_bounds__(256) probe_dmma_kernel(double* out, int iters,
     if (s == 12345.678) out[0] = s;
 }
 
+// ---- probes with the GEMM's own operand pattern (8x8 outer product per step: two fresh register operands per FMA,
+//      one reused), which is what the register file must sustain in a real micro-kernel ----
+__global__ void __launch_bounds__(256) probe_dmma_tile_kernel(double* out, int iters, double a0, double b0)
+{
+    double acc[8][4][2], a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = a0 + 1e-3 * (threadIdx.x + i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = b0 - 1e-3 * (threadIdx.x + j);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                             : "d"(a[i]), "d"(b[j]));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) probe_fma_tile_kernel(T* out, int iters, T a0, T b0)
+{
+    T acc[8][8], a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = a0 + T(1e-3) * T(threadIdx.x + i);
+        b[i] = b0 - T(1e-3) * T(threadIdx.x + i);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[j][r] = T(0);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[j][r] = fma_t(a[r], b[j], acc[j][r]);
+    }
+    T s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += acc[j][r];
+    if (s == T(12345.678)) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) probe_ffma2_tile_kernel(float* out, int iters, float a0, float b0)
+{
+    uint64_t acc[8][4], a[4], b[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float lo = a0 + 1e-3f * (threadIdx.x + i), hi = a0 - 1e-3f * (threadIdx.x + i);
+        asm("mov.b64 %0, {%1, %2};\n" : "=l"(a[i]) : "f"(lo), "f"(hi));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = b0 - 1e-3f * (threadIdx.x + j);
+        asm("mov.b64 %0, {%1, %1};\n" : "=l"(b[j]) : "f"(v));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[j][r] = 0ull;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(acc[j][r]) : "l"(a[r]), "l"(b[j]));
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s ^= acc[j][r];
+    if (s == 0x123456789abcdefull) out[0] = 1.f;
+}
+
 }  // namespace jb

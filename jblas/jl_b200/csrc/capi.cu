@@ -17,6 +17,7 @@
 #include "gemm_dmma.cuh"
 #include "gemm_dmma_tma.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_simt_f32x2.cuh"
 
 using namespace jb;
 
@@ -99,6 +100,26 @@ static cudaError_t attr_simt()
     cudaError_t e;
 #define SET(AL, AC)                                                                                               \
     e = cudaFuncSetAttribute(gemm_simt_kernel<T, Cfg, AL, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                             (int)Cfg::SMEM);                                                                     \
+    if (e != cudaSuccess) return e;
+    SET(false, false) SET(false, true) SET(true, false) SET(true, true)
+#undef SET
+    return cudaSuccess;
+}
+template <typename Cfg, bool ALIGNED, bool ACC>
+static int launch_simt_f32x2(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                             int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+{
+    gemm_simt_f32x2_kernel<Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
+        (float*)D, (const float*)A, (const float*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m);
+    return 0;
+}
+template <typename Cfg>
+static cudaError_t attr_simt_f32x2()
+{
+    cudaError_t e;
+#define SET(AL, AC)                                                                                               \
+    e = cudaFuncSetAttribute(gemm_simt_f32x2_kernel<Cfg, AL, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                              (int)Cfg::SMEM);                                                                     \
     if (e != cudaSuccess) return e;
     SET(false, false) SET(false, true) SET(true, false) SET(true, true)
@@ -193,6 +214,14 @@ static cudaError_t attr_dmma_tma()
              {launch_simt<T, CFG, true, false>, launch_simt<T, CFG, true, true>}},                                 \
             attr_simt<T, CFG>                                                                                      \
     }
+#define SIMT_F32X2_ENTRY(NAME, CFG, EFF)                                                                           \
+    {                                                                                                              \
+        NAME, JBLAS_B200_DT_F32, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
+            false, false,                                                                                          \
+            {{launch_simt_f32x2<CFG, false, false>, launch_simt_f32x2<CFG, false, true>},                          \
+             {launch_simt_f32x2<CFG, true, false>, launch_simt_f32x2<CFG, true, true>}},                           \
+            attr_simt_f32x2<CFG>                                                                                   \
+    }
 #define DMMA_ENTRY(NAME, CFG, EFF)                                                                                 \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F64, FAM_DMMA, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
@@ -216,6 +245,7 @@ using S64_64x64 = SimtCfg<double, 1, 2, 16, 4, 1>;
 using S32_128x128 = SimtCfg<float, 2, 4, 16, 4, 2>;
 using S32_128x64 = SimtCfg<float, 2, 2, 16, 4, 2>;
 using S32_64x64 = SimtCfg<float, 1, 2, 16, 4, 4>;
+using S32_128x128_k32 = SimtCfg<float, 2, 4, 32, 3, 2>;
 using D64_128x128 = DmmaCfg<2, 4, 16, 4>;
 using D64_128x64 = DmmaCfg<2, 2, 16, 4>;
 using D64_64x64 = DmmaCfg<1, 2, 16, 4>;
@@ -235,6 +265,10 @@ static const KernelInfo g_kernels[] = {
     /* 8 */ SIMT_ENTRY("simt_f32_64x64x16", float, JBLAS_B200_DT_F32, S32_64x64, 0.85f),
     /* 9 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x16_s6", T64_k16s6, 1.10f),
     /* 10 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x32_s3", T64_k32s3, 1.08f),
+    /* 11 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x16", S32_128x128, 1.20f),
+    /* 12 */ SIMT_F32X2_ENTRY("simt_f32x2_128x64x16", S32_128x64, 1.15f),
+    /* 13 */ SIMT_F32X2_ENTRY("simt_f32x2_64x64x16", S32_64x64, 1.00f),
+    /* 14 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x32", S32_128x128_k32, 1.21f),
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
@@ -685,6 +719,18 @@ int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms_out)
         } else if (kind == 2) {
             probe_ffma_kernel<32><<<blocks, threads, 0, s>>>((float*)out, iters, 1.0000001f, 1e-9f);
             flops = 2.0 * 32 * iters * (double)blocks * threads;
+        } else if (kind == 3) {  // DMMA, the GEMM warp-tile pattern (8x4 tiles, 2 warps per sub-partition)
+            probe_dmma_tile_kernel<<<g_ctx.num_sms, threads, 0, s>>>((double*)out, iters, 1.0000001, 1e-9);
+            flops = 2.0 * 256 * 32 * iters * (double)g_ctx.num_sms * (threads / 32);
+        } else if (kind == 4) {  // DFMA, 8x8 outer-product pattern
+            probe_fma_tile_kernel<double><<<g_ctx.num_sms, threads, 0, s>>>((double*)out, iters, 1.0000001, 1e-9);
+            flops = 2.0 * 64 * iters * (double)g_ctx.num_sms * threads;
+        } else if (kind == 5) {  // FFMA, 8x8 outer-product pattern, 2 CTAs per SM
+            probe_fma_tile_kernel<float><<<g_ctx.num_sms * 2, threads, 0, s>>>((float*)out, iters, 1.0000001f, 1e-9f);
+            flops = 2.0 * 64 * iters * (double)g_ctx.num_sms * 2 * threads;
+        } else if (kind == 6) {  // FFMA2 (fma.rn.f32x2), 8x8 outer-product pattern, 2 CTAs per SM
+            probe_ffma2_tile_kernel<<<g_ctx.num_sms * 2, threads, 0, s>>>((float*)out, iters, 1.0000001f, 1e-9f);
+            flops = 2.0 * 64 * iters * (double)g_ctx.num_sms * 2 * threads;
         } else {
             cudaFree(out);
             return fail(JBLAS_B200_EINVAL, "unknown probe kind %d", kind);

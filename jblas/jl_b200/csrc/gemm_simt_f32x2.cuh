@@ -1,0 +1,172 @@
+// gemm_simt_f32x2.cuh -- exact Float32 SIMT GEMM on Blackwell's packed FFMA2 (PTX fma.rn.f32x2), D = A*X or D += A*X.
+//
+// Why a second Float32 kernel: the scalar-FFMA kernel (gemm_simt.cuh) is bound by warp-scheduler issue slots and
+// register-file bank conflicts, not by the FMA pipe (ncu: fma pipe 59 %, dispatch stalls; profiles/).  sm_100 adds
+// fma.rn.f32x2 (SASS FFMA2): ONE instruction performs TWO independent IEEE fused multiply-adds on 64-bit register
+// pairs.  Half the issue slots for the same flops, and even/odd register pairs are bank-balanced by construction.
+// Each half is a correctly rounded fma, so every output element is still the reference chain
+//     d = A[i,1]*X[1,j];  d = fma(A[i,n], X[n,j], d)   (n ascending; src/gemm.jl:86,165)
+// and the result stays BIT-IDENTICAL to the oracle.
+//
+// Pairing: an accumulator pair is two consecutive ROWS (m, m+1) of one column.  A pairs come straight out of the
+// 16-byte shared-memory loads (m is contiguous in sA[k][m]); the X scalar of the column is duplicated into a
+// register pair once per k and reused by the four row-pairs of that column.
+#pragma once
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "tile_loader.cuh"
+
+namespace jb {
+
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(uint64_t& d, uint64_t a, uint64_t b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(d) : "l"(a), "l"(b));
+}
+
+// Same tiling contract as SimtCfg<float,...>: warp 64 x 32, thread 8 x 8 (rows i*32 + tx*4 + v, cols j*4 + ty).
+template <typename Cfg, bool ALIGNED, bool ACC>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS)
+gemm_simt_f32x2_kernel(float* __restrict__ D, const float* __restrict__ A, const float* __restrict__ X, int M, int N, int K,
+                       int64_t ldd, int64_t lda, int64_t ldx, int tiles_m, int tiles_n, int group_m)
+{
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
+    constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB, THREADS = Cfg::THREADS;
+    static_assert(Cfg::VEC == 4, "Float32 only");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* smem = reinterpret_cast<float*>(smem_raw);
+
+    int tm, tn;
+    raster(blockIdx.x, tiles_m, tiles_n, group_m, tm, tn);
+    const int m0 = tm * BM, n0 = tn * BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % (BM / 64), wn = warp / (BM / 64);
+    const int tx = lane & 7, ty = lane >> 3;
+    const int row_base = wm * 64 + tx * 4;
+    const int col_base = wn * 32 + ty;
+
+    uint64_t acc[8][4];  // [column j][row pair: rows (i*32 + 2h, +1) for pair index i*2 + h]
+    const bool d_vec_ok = (ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+    const bool interior = (m0 + BM <= M) && (n0 + BN <= N);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int gn = n0 + col_base + j * 4;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if constexpr (ACC) {
+                const int gm = m0 + row_base + (p >> 1) * 32 + (p & 1) * 2;
+                float lo = (gm < M && gn < N) ? D[(size_t)gn * ldd + gm] : 0.f;
+                float hi = (gm + 1 < M && gn < N) ? D[(size_t)gn * ldd + gm + 1] : 0.f;
+                acc[j][p] = pack_f32x2(lo, hi);
+            } else {
+                acc[j][p] = 0x8000000080000000ull;  // (-0.0f, -0.0f): fma(a, b, -0) == a*b exactly
+            }
+        }
+    }
+
+    const int KT = (K + BK - 1) / BK;
+    auto stageA = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS; };
+    auto stageB = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS + BK * LDA; };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT)
+            load_stage<float, BM, BN, BK, LDA, LDB, THREADS, ALIGNED>(stageA(s), stageB(s), A, X, lda, ldx, M, N, K, m0, n0,
+                                                                       s * BK, tid);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT)
+                load_stage<float, BM, BN, BK, LDA, LDB, THREADS, ALIGNED>(stageA(nk % STAGES), stageB(nk % STAGES), A, X,
+                                                                           lda, ldx, M, N, K, m0, n0, nk * BK, tid);
+            cp_async_commit();
+        }
+        const float* sA = stageA(kt % STAGES) + row_base;
+        const float* sB = stageB(kt % STAGES) + col_base * LDB;
+        const int kmax = min(BK, K - kt * BK);
+        if (kmax == BK) {
+#pragma unroll
+            for (int kc = 0; kc < BK; kc += 2) {
+                float2 b[8];  // X[k, k+1] of the thread's 8 columns
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = *reinterpret_cast<const float2*>(sB + j * 4 * LDB + kc);
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv) {
+                    ulonglong2 a[2];  // rows (0,1),(2,3) and (32,33),(34,35) of the thread, as packed pairs
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const ulonglong2*>(sA + (kc + kv) * LDA + i * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float bs = kv ? b[j].y : b[j].x;
+                        const uint64_t bb = pack_f32x2(bs, bs);
+                        ffma2(acc[j][0], a[0].x, bb);
+                        ffma2(acc[j][1], a[0].y, bb);
+                        ffma2(acc[j][2], a[1].x, bb);
+                        ffma2(acc[j][3], a[1].y, bb);
+                    }
+                }
+            }
+        } else {  // K tail: bounded loop, no padded multiplies
+            for (int k = 0; k < kmax; ++k) {
+                ulonglong2 a[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const ulonglong2*>(sA + k * LDA + i * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float bs = sB[j * 4 * LDB + k];
+                    const uint64_t bb = pack_f32x2(bs, bs);
+                    ffma2(acc[j][0], a[0].x, bb);
+                    ffma2(acc[j][1], a[0].y, bb);
+                    ffma2(acc[j][2], a[1].x, bb);
+                    ffma2(acc[j][3], a[1].y, bb);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- store (src/gemm.jl:3-11: plain overwrite, column-major) ----
+    if (interior && d_vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float* dcol = D + (size_t)(n0 + col_base + j * 4) * ldd + m0 + row_base;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                ulonglong2 o;
+                o.x = acc[j][2 * i];
+                o.y = acc[j][2 * i + 1];
+                *reinterpret_cast<ulonglong2*>(dcol + i * 32) = o;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gn = n0 + col_base + j * 4;
+            if (gn >= N) continue;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int gm = m0 + row_base + (p >> 1) * 32 + (p & 1) * 2;
+                float lo, hi;
+                unpack_f32x2(acc[j][p], lo, hi);
+                if (gm < M) D[(size_t)gn * ldd + gm] = lo;
+                if (gm + 1 < M) D[(size_t)gn * ldd + gm + 1] = hi;
+            }
+        }
+    }
+}
+
+}  // namespace jb

@@ -36,8 +36,18 @@ def to_dev(a):
 
     rows, cols = a.shape
     ld = a.strides[1] // a.itemsize if cols > 1 else max(rows, 1)
-    base = a.base if (a.base is not None and isinstance(a.base, np.ndarray) and a.base.shape[0] == ld) else a
-    store = torch.from_numpy(np.ascontiguousarray(base.T)).cuda()  # (cols, ld) row-major == column-major (ld, cols)
+    if ld == rows or cols <= 1:
+        parent = np.asfortranarray(a)
+        ld = max(rows, 1)
+    else:  # strided view: rebuild the (ld, cols) column-major parent, padding rows included (NaN where unknown)
+        parent = np.full((ld, cols), np.nan, dtype=a.dtype, order="F")
+        b = a.base
+        if (isinstance(b, np.ndarray) and b.shape == (ld, cols) and b.flags.f_contiguous and b.dtype == a.dtype
+                and b.ctypes.data == a.ctypes.data):
+            parent[...] = b
+        else:
+            parent[:rows, :] = a
+    store = torch.from_numpy(np.ascontiguousarray(parent.T)).cuda()  # (cols, ld) row-major == column-major (ld, cols)
     return store.t()[:rows, :]
 
 

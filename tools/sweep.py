@@ -33,8 +33,8 @@ def time_call(fn, reps, warm=2):
 def main():
     jb.init(0)
     res = {"probes": {}, "shapes": {}}
-    for kind in ("dfma", "dmma", "ffma"):
-        vals = [jb.probe_pipe(kind, 4000 if kind == "dmma" else 40000)[0] for _ in range(2)]
+    for kind in ("dfma", "dmma", "ffma", "dmma_tile", "dfma_tile", "ffma_tile", "ffma2_tile"):
+        vals = [jb.probe_pipe(kind, 4000 if "dmma" in kind else (10000 if "tile" in kind else 40000))[0] for _ in range(2)]
         res["probes"][kind] = vals
         print("probe", kind, vals, flush=True)
     names = jb.kernel_names()
