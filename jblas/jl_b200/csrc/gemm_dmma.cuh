@@ -71,6 +71,7 @@ gemm_dmma_kernel(double* __restrict__ D, const double* __restrict__ A, const dou
             }
 
     const int KT = (K + BK - 1) / BK;
+    const bool k_tail = (K % BK) != 0;
     auto stageA = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS; };
     auto stageB = [&](int s) { return smem + (size_t)s * Cfg::STAGE_ELEMS + BK * LDA; };
 
@@ -92,8 +93,8 @@ gemm_dmma_kernel(double* __restrict__ D, const double* __restrict__ A, const dou
                                                                             lda, ldx, M, N, K, m0, n0, nk * BK, tid);
             cp_async_commit();
         }
-        // Zero padding beyond K (cp.async zero-fill) is multiplied here: a*0 + c leaves c unchanged except that a
-        // -0.0 accumulator may become +0.0; acceptable under this kernel's tolerance contract.
+        // Zero padding beyond K (cp.async zero-fill) is multiplied here; the X side of padded k is replaced by -0.0
+        // below so that the padded product is -0.0 and leaves every accumulator (including -0.0) unchanged.
         const double* sA = stageA(kt % STAGES) + t * LDA + wm * 64 + g;
         const double* sB = stageB(kt % STAGES) + (wn * 32 + g) * LDB + t;
 #pragma unroll
@@ -103,6 +104,10 @@ gemm_dmma_kernel(double* __restrict__ D, const double* __restrict__ A, const dou
             for (int mi = 0; mi < 8; ++mi) a[mi] = sA[k4 * LDA + mi * 8];
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) b[ni] = sB[ni * 8 * LDB + k4];
+            if (k_tail && kt == KT - 1 && (kt * BK + k4 + t) >= K) {  // padded k: make the product -0.0 (c + -0.0 == c)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) b[ni] = -0.0;
+            }
 #pragma unroll
             for (int mi = 0; mi < 8; ++mi)
 #pragma unroll

@@ -184,6 +184,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     for (int k4 = 0; k4 < 4; ++k4)
         offB[k4] = (uint32_t)((wn * 32 + sg_g) * 128 + (((k4 * 2 + (t >> 1)) ^ sg_g) << 4) + (t & 1) * 8);
 
+    const bool k_tail = (K % BK) != 0;
     int s = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -222,6 +223,12 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni)
                         b[ni] = lds_f64(st + offB[k4] + (sub * Cfg::SUB_BYTES + Cfg::A_SUB_BYTES + ni * 1024));
+                    // K tail: TMA zero-fills k >= K in both operands; (+0)*(+0) added to a -0.0 accumulator would give
+                    // +0.0.  Feeding -0.0 on the X side makes the padded product -0.0, and c + (-0.0) == c for every c.
+                    if (k_tail && kt == KT - 1 && (kt * BK + sub * 16 + k4 * 4 + t) >= K) {
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) b[ni] = -0.0;
+                    }
 #pragma unroll
                     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll

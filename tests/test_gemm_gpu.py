@@ -177,6 +177,36 @@ def test_dmma_within_reference_tolerance(jb, shape):
         json.dump(report, f, indent=1)
 
 
+@pytest.mark.parametrize("shape", [(70, 37, 9), (72, 36, 10), (256, 130, 64), (128, 2, 128)], ids=lambda s: "x".join(map(str, s)))
+def test_dmma_is_bit_identical_to_the_chain_on_b200(jb, shape):
+    """MEASURED hardware property, asserted so a regression is loud: B200's DMMA.8x8x4 accumulates its 4 products as
+    sequential single-rounded FMAs in ascending k, so the tensor path reproduces the reference chain bit for bit --
+    including signed zeros, exact cancellation, subnormals and the zero-padded K tail (padded X side is -0.0)."""
+    M, K, N = shape
+    A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
+    A[0, :] = 0.0
+    X[:, 0] = -np.abs(X[:, 0])          # every product -0.0 -> result must stay -0.0
+    A[1, :] = np.tile([1.0, -1.0], K)[:K]
+    X[:, 1] = 1.0                       # exact cancellation (K even) -> +0.0
+    A[4, :] *= 1e-160
+    X[:, 2] *= 1e-160                   # subnormal / underflowing products
+    want = oracle.oracle_gemm(A, X)
+    assert np.signbit(want[0, 0]) and want[0, 0] == 0.0
+    for sel in _dmma_selectors(jb):
+        name = jb.kernel_names()[sel - jb.EXPLICIT_BASE]
+        if "tma" in name and (M % 2 or K % 2):
+            continue
+        got = _run_dev(jb, A, X, sel)
+        assert bits_equal(got, want), name
+    D0 = randn_f((M, N), seed=5)
+    want_acc = oracle.oracle_gemm(A, X, D0.copy(order="F"), accumulate=True)
+    for sel in _dmma_selectors(jb):
+        name = jb.kernel_names()[sel - jb.EXPLICIT_BASE]
+        if "tma" in name and (M % 2 or K % 2):
+            continue
+        assert bits_equal(_run_dev(jb, A, X, sel, accumulate_into=D0), want_acc), name
+
+
 def test_dmma_accumulate_and_strided(jb):
     M, K, N = 150, 50, 66
     A, X = randn_f((M, K), ld=151), randn_f((K, N), seed=SEED_X, ld=50)
