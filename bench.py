@@ -55,7 +55,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -272,14 +272,17 @@ def run_gpu(args):
     if rank == 0:
         peaks, peak_src = load_peaks()
         if dtype == "float64":
-            dfma, _ = jb.probe_pipe("dfma", 40000)
-            dmma, _ = jb.probe_pipe("dmma", 4000)
+            # register-resident probes: the DMMA warp-tile pattern (what the tensor pipe can sustain with free operands)
+            # and DFMA in the 8x8 outer-product pattern (what a SIMT micro-kernel can sustain)
+            dmma, _ = jb.probe_pipe("dmma_tile", 4000)
+            dfma, _ = jb.probe_pipe("dfma_tile", 10000)
             peak, nominal = max(dfma, dmma), FP64_NOMINAL_TFLOPS
-            probe = {"dfma_tflops": dfma, "dmma_tflops": dmma}
+            probe = {"dmma_tile_tflops": dmma, "dfma_tile_tflops": dfma}
         else:
             ffma, _ = jb.probe_pipe("ffma", 40000)
-            peak, nominal = ffma, FP32_NOMINAL_TFLOPS
-            probe = {"ffma_tflops": ffma}
+            ffma2, _ = jb.probe_pipe("ffma2_tile", 10000)
+            peak, nominal = max(ffma, ffma2), FP32_NOMINAL_TFLOPS
+            probe = {"ffma_chain_tflops": ffma, "ffma2_tile_tflops": ffma2}
         per_launch_flops = flops_step / world / sg.launches_per_call()
         # kernel-only duration: time the local kernel launches alone on this stream (no collective)
         k0, k1 = sg.panels[0]

@@ -415,11 +415,12 @@ static int ensure_ws(int i, size_t bytes)
     return 0;
 }
 
-// Synchronous host-pointer GEMM: the literal drop-in for jmul!(D, A, X).
-//   copy stream : X (all), then A in K-panels           (H2D)
-//   compute     : panel p multiplies A[:, kp] * X[kp, :] into the device D with accumulate = (p > 0) -- ascending
-//                 k per element, so the chain (and the bits) are those of a single launch
-//   copy stream : D back by column blocks               (D2H)
+// Synchronous host-pointer GEMM: the literal drop-in for jmul!(D, A, X).  Everything is pipelined over K PANELS:
+//   copy stream : for panel p:  A[:, kp] and X[kp, :]   (H2D; panel p+1 travels while panel p is multiplied)
+//   compute     : D (+)= A[:, kp] * X[kp, :]  with accumulate = (p > 0): ascending k per element, so the chain (and,
+//                 for the exact kernels, every bit) is that of a single launch (kernel! semantics, src/kernels.jl:226)
+//   last panel  : split by column blocks of D; block b goes back to the host (D2H) while block b+1 is computed
+// With pinned caller buffers (jblas_b200_host_register) PCIe and the tensor pipe overlap almost completely.
 template <typename T>
 static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
                      int64_t ldx, int accumulate, int selector)
@@ -429,7 +430,7 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
     if (int rc = validate(D, A, X, M, K, N, ldd, lda, ldx)) return rc;
     if (M == 0 || N == 0) return 0;
     const size_t es = sizeof(T);
-    // device copies are dense with even leading dimensions so the 16-byte staging path applies
+    // device copies are dense with even leading dimensions so the 16-byte / TMA staging paths apply
     const int vec = 16 / (int)es;
     const int64_t dM = (M + vec - 1) / vec * vec, dK = (K + vec - 1) / vec * vec;
     if (int rc = ensure_ws(0, (size_t)dM * N * es)) return rc;
@@ -443,29 +444,54 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
     cudaStream_t cs = g_ctx.copy_stream, ks = g_ctx.stream;
     CUDA_TRY(cudaEventRecord(g_ctx.ev0, cs));
     if (accumulate) CUDA_TRY(cudaMemcpy2DAsync(dD, dM * es, D, ldd * es, M * es, N, cudaMemcpyHostToDevice, cs));
-    if (K > 0) CUDA_TRY(cudaMemcpy2DAsync(dX, dK * es, X, ldx * es, K * es, N, cudaMemcpyHostToDevice, cs));
-    // K-panels of A: big enough to amortise launches, small enough to overlap PCIe with compute
-    int64_t kp = K;
-    if ((size_t)M * K * es > ((size_t)64 << 20)) {
-        kp = (int64_t)(((size_t)64 << 20) / ((size_t)M * es));
-        kp = kp / 64 * 64;
-        if (kp < 64) kp = 64;
-    }
     if (K == 0) {
-        if (int rc = gemm_dev<T>(dtype, dD, dA, dX, M, 0, N, dM, dM, dK > 0 ? dK : 1, accumulate, selector, ks)) return rc;
-    }
-    for (int64_t k0 = 0; k0 < K; k0 += kp) {
-        int64_t kc = (K - k0 < kp) ? (K - k0) : kp;
-        CUDA_TRY(cudaMemcpy2DAsync(dA + k0 * dM, dM * es, A + k0 * lda, lda * es, M * es, kc, cudaMemcpyHostToDevice, cs));
         CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
         CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
-        if (int rc = gemm_dev<T>(dtype, dD, dA + k0 * dM, dX + k0, M, kc, N, dM, dM, dK, (accumulate || k0 > 0) ? 1 : 0,
-                                 selector, ks))
-            return rc;
+        if (int rc = gemm_dev<T>(dtype, dD, dA, dX, M, 0, N, dM, dM, 1, accumulate, selector, ks)) return rc;
     }
-    CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
-    CUDA_TRY(cudaStreamWaitEvent(cs, g_ctx.ev_copy, 0));
-    CUDA_TRY(cudaMemcpy2DAsync(D, ldd * es, dD, dM * es, M * es, N, cudaMemcpyDeviceToHost, cs));
+    // K panels: ~64 MiB of A (+ the matching rows of X) per panel -- big enough to amortise launches and keep the
+    // kernels efficient, small enough that the first multiply starts early
+    int64_t kp = K;
+    const size_t panel_bytes = (size_t)64 << 20;
+    if (K > 0 && (size_t)(M + N) * K * es > 2 * panel_bytes) {
+        kp = (int64_t)(panel_bytes / ((size_t)(M > N ? M : N) * es));
+        kp = kp / 64 * 64;
+        if (kp < 256) kp = 256;
+        if (kp > K) kp = K;
+    }
+    // column blocks of the LAST panel (D2H overlap): up to 4 blocks of a multiple of 128 columns
+    int64_t nb = N;
+    if ((size_t)M * N * es > panel_bytes) {
+        nb = ((N + 3) / 4 + 127) / 128 * 128;
+        if (nb > N) nb = N;
+    }
+    for (int64_t k0 = 0; k0 < K; k0 += kp) {
+        const int64_t kc = (K - k0 < kp) ? (K - k0) : kp;
+        const bool last = (k0 + kc >= K);
+        const int acc = (accumulate || k0 > 0) ? 1 : 0;
+        CUDA_TRY(cudaMemcpy2DAsync(dA + k0 * dM, dM * es, A + k0 * lda, lda * es, M * es, kc, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpy2DAsync(dX + k0, dK * es, X + k0, ldx * es, kc * es, N, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
+        CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
+        if (!last) {
+            if (int rc = gemm_dev<T>(dtype, dD, dA + k0 * dM, dX + k0, M, kc, N, dM, dM, dK, acc, selector, ks)) return rc;
+        } else {
+            for (int64_t n0 = 0; n0 < N; n0 += nb) {
+                const int64_t nc = (N - n0 < nb) ? (N - n0) : nb;
+                if (int rc = gemm_dev<T>(dtype, dD + n0 * dM, dA + k0 * dM, dX + k0 + n0 * dK, M, kc, nc, dM, dM, dK, acc,
+                                         selector, ks))
+                    return rc;
+                CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
+                CUDA_TRY(cudaStreamWaitEvent(cs, g_ctx.ev_copy, 0));
+                CUDA_TRY(cudaMemcpy2DAsync(D + n0 * ldd, ldd * es, dD + n0 * dM, dM * es, M * es, nc, cudaMemcpyDeviceToHost, cs));
+            }
+        }
+    }
+    if (K == 0) {
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
+        CUDA_TRY(cudaStreamWaitEvent(cs, g_ctx.ev_copy, 0));
+        CUDA_TRY(cudaMemcpy2DAsync(D, ldd * es, dD, dM * es, M * es, N, cudaMemcpyDeviceToHost, cs));
+    }
     CUDA_TRY(cudaEventRecord(g_ctx.ev1, cs));
     CUDA_TRY(cudaStreamSynchronize(cs));
     CUDA_TRY(cudaStreamSynchronize(ks));

@@ -256,12 +256,23 @@ def test_host_pointer_entry_matches_oracle(jb, dt):
 
 
 def test_host_pointer_k_panel_pipeline_is_bit_identical(jb):
-    """A > 64 MiB is staged in K panels with accumulate passes; per-element k order is unchanged."""
-    M, K, N = 4096, 2304, 512  # A = 72 MiB -> 2 panels
+    """Large operands are staged in K panels (accumulate passes) and the last panel is split into column blocks whose
+    D2H overlaps the next block's multiply; per-element k order -- and every bit -- is unchanged."""
+    M, K, N = 4096, 4608, 2304  # 3 K-panels of <= 2048, D = 72 MiB -> 4 column blocks
     A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
+    want = oracle.oracle_gemm(A, X)
     D = nan_f((M, N))
     jb.jmul_(D, A, X, kernel=jb.F64_SIMT)
-    assert bits_equal(D, oracle.oracle_gemm(A, X))
+    assert bits_equal(D, want)
+    D2 = nan_f((M, N), ld=M + 6)
+    jb.jmul_(D2, randn_f((M, K), ld=M + 2), X)  # AUTO (DMMA/TMA) through the same pipeline, strided host matrices
+    assert bits_equal(D2, want) and np.isnan(D2.base[M:, :]).all()
+    D0 = randn_f((M, N), seed=9)
+    D3 = D0.copy(order="F")
+    from jblas.jl_b200 import api
+
+    api._gemm(D3, A, X, True, jb.F64_SIMT)  # accumulate through the pipeline: old D uploaded first
+    assert bits_equal(D3, oracle.oracle_gemm(A, X, D0.copy(order="F"), accumulate=True))
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Summarise .ncu-rep captures (brought back in gpurun_out/) into small tracked text files under profiles/.
+
+    python tools/ncu_summary.py gpurun_out/prof_dmma_tma_k32.ncu-rep profiles/r1_dmma_tma_k32.txt ["free-text note"]
+
+Runs here on the CPU box (`ncu -i ... --page raw --csv` needs no GPU)."""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum",
+    "sm__cycles_elapsed.avg.per_second",
+    "launch__grid_size",
+    "launch__block_size",
+    "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic",
+    "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum",
+    "dram__bytes_read.sum",
+    "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    note = sys.argv[3] if len(sys.argv) > 3 else ""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    lines = [f"# ncu --set full --clock-control none capture: {rep}", f"# {note}" if note else "#"]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        lines.append("")
+        lines.append("kernel: " + d.get("Kernel Name", "?"))
+        for k in KEYS:
+            if k in d:
+                lines.append(f"  {k:90s} {d[k]:>20s} {units[hdr.index(k)]}")
+    open(out, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main()
