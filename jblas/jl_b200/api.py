@@ -238,6 +238,8 @@ def plan(M: int, K: int, N: int, dtype="float64", kernel: int | None = None, ldd
     check(L.jblas_b200_plan(dt, M, K, N, ldd or M, lda or M, ldx or K, kernel, out))
     name = L.jblas_b200_kernel_name(int(out[0])).decode()
     staging = "TMA cp.async.bulk.tensor, 128B swizzle" if "tma" in name else ("cp.async 16B" if out[9] else "cp.async element-wise")
+    if out[9] == 2:
+        staging += " (after re-aligning the ragged operand into scratch)"
     return {
         "kernel": name,
         "kernel_index": int(out[0]),

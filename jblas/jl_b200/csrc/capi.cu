@@ -249,8 +249,12 @@ using S32_128x128_k32 = SimtCfg<float, 2, 4, 32, 3, 2>;
 using D64_128x128 = DmmaCfg<2, 4, 16, 4>;
 using D64_128x64 = DmmaCfg<2, 2, 16, 4>;
 using D64_64x64 = DmmaCfg<1, 2, 16, 4>;
-using T64_k16s6 = DmmaTmaCfg<1, 6>;  // 6 stages of 32 KiB
-using T64_k32s3 = DmmaTmaCfg<2, 3>;  // 3 stages of 64 KiB
+//                             WARPS_M WARPS_N MI NI KSUB STAGES
+using T64_k16s6 = DmmaTmaCfg<2, 4, 8, 4, 1, 6>;      // 128x128, 6 stages of 32 KiB
+using T64_k32s3 = DmmaTmaCfg<2, 4, 8, 4, 2, 3>;      // 128x128, 3 stages of 64 KiB
+using T64_128x64 = DmmaTmaCfg<2, 2, 8, 4, 2, 4>;     // 4 warps of 64x32, 4 stages of 48 KiB
+using T64_96x64 = DmmaTmaCfg<2, 2, 6, 4, 2, 4>;      // 4 warps of 48x32: tile count just under #SMs on ragged shapes
+using T64_64x64_k64 = DmmaTmaCfg<2, 2, 4, 4, 4, 3>;  // 4 warps of 32x32, BK = 64: tall-skinny (K = 64 is ONE stage)
 
 // NOTE: indices are part of the tuning interface (selector 100+i); append, do not reorder.
 static const KernelInfo g_kernels[] = {
@@ -269,6 +273,9 @@ static const KernelInfo g_kernels[] = {
     /* 12 */ SIMT_F32X2_ENTRY("simt_f32x2_128x64x16", S32_128x64, 1.22f),
     /* 13 */ SIMT_F32X2_ENTRY("simt_f32x2_64x64x16", S32_64x64, 1.18f),
     /* 14 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x32", S32_128x128_k32, 1.28f),
+    /* 15 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4", T64_128x64, 1.12f),
+    /* 16 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4", T64_96x64, 1.08f),
+    /* 17 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x64_s3", T64_64x64_k64, 1.00f),
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
@@ -360,6 +367,15 @@ __global__ void zero_fill_kernel(T* D, int64_t M, int64_t N, int64_t ldd)
         D[(i / M) * ldd + (i % M)] = T(0);
 }
 
+// 2-D copy into a buffer with an aligned leading dimension (threads along the contiguous rows: coalesced both ways)
+template <typename T>
+__global__ void realign_kernel(T* __restrict__ dst, int64_t ldd, const T* __restrict__ src, int64_t lds, int rows, int cols)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int c = blockIdx.y; c < cols; c += gridDim.y) dst[(size_t)c * ldd + r] = src[(size_t)c * lds + r];
+}
+
 static int set_all_attrs()
 {
     if (g_ctx.attrs_set) return 0;
@@ -384,13 +400,41 @@ static int gemm_dev(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t 
         }
         return 0;
     }
+    // Ragged leading dimensions (e.g. M = 1023 doubles per column) break the 16-byte alignment TMA and 16-byte cp.async
+    // need.  For products big enough to matter, the misaligned operand is first copied into a stream-ordered scratch
+    // buffer with an even leading dimension (HBM-speed pass, a few % of the GEMM), then the fast path runs.
+    const int vec = 16 / (int)sizeof(T);
+    T* tmpA = nullptr;
+    T* tmpX = nullptr;
+    if (2.0 * (double)M * (double)N * (double)K >= 1.0e9) {
+        if (!is_aligned16(A) || lda % vec) {
+            const int64_t ld2 = (M + vec - 1) / vec * vec;
+            CUDA_TRY(cudaMallocAsync((void**)&tmpA, (size_t)ld2 * K * sizeof(T), s));
+            realign_kernel<T><<<dim3((unsigned)((M + 255) / 256), (unsigned)(K < 65535 ? K : 65535)), 256, 0, s>>>(tmpA, ld2, A, lda, (int)M, (int)K);
+            g_launches++;
+            A = tmpA;
+            lda = ld2;
+        }
+        if (!is_aligned16(X) || ldx % vec) {
+            const int64_t ld2 = (K + vec - 1) / vec * vec;
+            CUDA_TRY(cudaMallocAsync((void**)&tmpX, (size_t)ld2 * N * sizeof(T), s));
+            realign_kernel<T><<<dim3((unsigned)((K + 255) / 256), (unsigned)(N < 65535 ? N : 65535)), 256, 0, s>>>(tmpX, ld2, X, ldx, (int)K, (int)N);
+            g_launches++;
+            X = tmpX;
+            ldx = ld2;
+        }
+    }
     Plan p;
-    if (int rc = make_plan(dtype, M, K, N, lda, ldx, A, X, selector, &p)) return rc;
-    if (int rc = set_all_attrs()) return rc;
-    const KernelInfo& k = g_kernels[p.kidx];
-    if (int rc = k.launch[p.aligned ? 1 : 0][accumulate ? 1 : 0](D, A, X, (int)M, (int)N, (int)K, ldd, lda, ldx, p.tiles_m,
-                                                                 p.tiles_n, p.group_m, s))
-        return rc;
+    int rc = make_plan(dtype, M, K, N, lda, ldx, A, X, selector, &p);
+    if (!rc) rc = set_all_attrs();
+    if (!rc) {
+        const KernelInfo& k = g_kernels[p.kidx];
+        rc = k.launch[p.aligned ? 1 : 0][accumulate ? 1 : 0](D, A, X, (int)M, (int)N, (int)K, ldd, lda, ldx, p.tiles_m, p.tiles_n,
+                                                             p.group_m, s);
+    }
+    if (tmpA) cudaFreeAsync(tmpA, s);
+    if (tmpX) cudaFreeAsync(tmpX, s);
+    if (rc) return rc;
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -709,12 +753,19 @@ int jblas_b200_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t ldd, int
     if (M <= 0 || N <= 0 || K <= 0 || ldd < M || lda < M || ldx < K) return fail(JBLAS_B200_EINVAL, "bad dimensions");
     Plan p;
     // alignment of device bases is assumed (cudaMalloc gives 256 B); leading dimensions decide the staging path
+    const int vec = dtype == JBLAS_B200_DT_F64 ? 2 : 4;
+    bool realigned = false;
+    if (2.0 * (double)M * (double)N * (double)K >= 1.0e9 && (lda % vec || ldx % vec)) {  // same rule as gemm_dev
+        lda = (lda + vec - 1) / vec * vec;
+        ldx = (ldx + vec - 1) / vec * vec;
+        realigned = true;
+    }
     if (int rc = make_plan(dtype, M, K, N, lda, ldx, nullptr, nullptr, selector, &p)) return rc;
     const KernelInfo& k = g_kernels[p.kidx];
     out[0] = p.kidx; out[1] = k.bm; out[2] = k.bn; out[3] = k.bk; out[4] = k.stages; out[5] = k.threads;
     out[6] = (int64_t)p.tiles_m * p.tiles_n;
     if (k.persistent && out[6] > (g_ctx.num_sms > 0 ? g_ctx.num_sms : 148)) out[6] = g_ctx.num_sms > 0 ? g_ctx.num_sms : 148;
-    out[7] = p.group_m; out[8] = (int64_t)k.smem; out[9] = p.aligned ? 1 : 0;
+    out[7] = p.group_m; out[8] = (int64_t)k.smem; out[9] = realigned ? 2 : (p.aligned ? 1 : 0);
     return 0;
 }
 const char* jblas_b200_kernel_name(int kidx) { return (kidx >= 0 && kidx < NUM_KERNELS) ? g_kernels[kidx].name : ""; }

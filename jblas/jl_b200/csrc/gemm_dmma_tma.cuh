@@ -1,31 +1,32 @@
 // gemm_dmma_tma.cuh -- FP64 tensor-core GEMM, warp-specialised TMA producer / DMMA consumers, persistent CTAs.
 //
-// This is the main FP64 kernel.  It replaces, in one design, the three things north_star names:
+// This is the main FP64 kernel family.  It replaces, in one design, the three things north_star names:
 //   * "packing buffers / cache blocking" (the reference has only software prefetch, src/memory_management.jl:181-277,
 //     and an uncalled planner, :78-140)  ->  TMA (cp.async.bulk.tensor) stages A and X tiles into a multi-stage
 //     shared-memory ring; no thread spends issue slots on copies;
 //   * the register-tile SIMD micro-kernel (src/gemm.jl:149-170, src/kernels.jl:212-275)  ->  mma.sync.m8n8k4.f64
-//     (SASS DMMA.8x8x4), 8x4 tiles per warp, accumulators in registers (FP64 has no tcgen05/TMEM kind);
+//     (SASS DMMA.8x8x4), MI x NI tiles per warp, accumulators in registers (FP64 has no tcgen05/TMEM kind);
 //   * the two tile loops of jmul! (src/gemm.jl:313)  ->  a persistent grid (one CTA per SM) walking a rasterised
 //     tile list, so the producer runs ahead across tile boundaries and the pipeline never drains.
 //
-// Roles (384 threads = 3 warpgroups): warps 0..7 consume (2 x 4 warp grid, 64 x 32 per warp), warp 8 lane 0 produces;
-// setmaxnreg moves the producer warpgroup's registers to the consumers.
+// Roles: WARPS_M x WARPS_N consumer warps (4 or 8 = 1 or 2 warpgroups) + one producer warpgroup whose first lane
+// issues every TMA of the CTA.  With 8 consumer warps, setmaxnreg moves the idle producer warpgroup's registers to the
+// consumers (a lone 9th warp would put 3 warps on one SM sub-partition and cap EVERY thread at 168 registers).
 // Synchronisation is mbarrier-only in the main loop: full[s] (TMA complete_tx) and empty[s] (one arrive per
 // consumer warp); no CTA-wide barrier after start-up.
 //
 // Shared-memory layout = what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B (16-byte chunk index XOR row&7):
-//   A sub-tile: 8 boxes (16 m x 16 k), box = 16 rows (k) of 128 B (16 doubles of m)
-//   X sub-tile: 1 box  (16 k x 128 n),     128 rows (n) of 128 B (16 doubles of k)
+//   A sub-tile: BM/16 boxes (16 m x 16 k), box = 16 rows (k) of 128 B (16 doubles of m)
+//   X sub-tile: 1 box (16 k x BN n),       BN rows (n) of 128 B (16 doubles of k)
 // DMMA fragment loads are 8-byte LDS; a half-warp (16 lanes) must hit 16 distinct 8-byte slots of the 128-byte
 // bank window.  With the hardware swizzle that holds if the LOGICAL rows/columns of an MMA tile are permuted:
 //   A: MMA row g of sub-tile `sub` of a 16-row box is physical row  pi(g) = (g&1) + 8*((g>>1)&1) + 2*(g>>2) + 4*sub
 //   X: MMA column g of an 8-column group is physical column          sg(g) = 2*(g&3) + (g>>2)
-// (derivation in DESIGN.md "bank-conflict-free fragments"); ncu confirms 0 shared-memory bank conflicts.
+// (derivation in DESIGN.md "bank-conflict-free fragments"); ncu: 0.05 % of shared wavefronts conflict.
 // The accumulator fragment is un-permuted on the way out with the same two maps.
 //
-// Numerics: ascending k, 4 at a time, starting from -0.0 (or the old D when ACC); contract = the reference
-// tolerance 2*K*eps*(|A||X|); measured against the oracle in tests/test_gemm_gpu.py.
+// Numerics: ascending k, 4 at a time, starting from -0.0 (or the old D when ACC).  Contract = the reference tolerance
+// 2*K*eps*(|A||X|); measured on B200: bit-identical to the sequential fma chain (tests/test_gemm_gpu.py).
 #pragma once
 #include <cuda.h>
 
@@ -84,21 +85,56 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map)
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
 }
 
-template <int KSUB_, int STAGES_>
+// CTA tile = (WARPS_M * MI * 8) x (WARPS_N * NI * 8); warp tile = MI x NI DMMA tiles (MI even: a 16-row box = 2 tiles).
+template <int WARPS_M_, int WARPS_N_, int MI_, int NI_, int KSUB_, int STAGES_>
 struct DmmaTmaCfg {
-    static constexpr int BM = 128, BN = 128, KSUB = KSUB_, BK = 16 * KSUB_, STAGES = STAGES_;
-    static constexpr int CONSUMER_WARPS = 8;
-    // 3 warpgroups: two consumer warpgroups + one producer warpgroup (only its first lane works).  A 9th warp alone
-    // would put 3 warps on one SM sub-partition and cap EVERY thread at 168 registers; with whole warpgroups the
-    // producer donates its registers to the consumers via setmaxnreg (40 vs 232 per thread: 32*(232+232+40) <= 16384).
+    static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, MI = MI_, NI = NI_;
+    static constexpr int BM = WARPS_M * MI * 8, BN = WARPS_N * NI * 8, KSUB = KSUB_, BK = 16 * KSUB_, STAGES = STAGES_;
+    static constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
+    static_assert(MI % 2 == 0 && (CONSUMER_WARPS == 4 || CONSUMER_WARPS == 8) && BN <= 256, "unsupported tile");
     static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
+    static constexpr bool REALLOC_REGS = CONSUMER_WARPS == 8;  // 384 threads: 168 regs at launch -> 232 / 40
     static constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;
-    static constexpr int A_SUB_BYTES = BM * 16 * 8;  // 8 boxes x 2 KiB
-    static constexpr int B_SUB_BYTES = BN * 16 * 8;  // 1 box of 16 KiB
+    static constexpr int A_SUB_BYTES = BM * 128;  // BM/16 boxes x 2 KiB
+    static constexpr int B_SUB_BYTES = BN * 128;  // 1 box
     static constexpr int SUB_BYTES = A_SUB_BYTES + B_SUB_BYTES;
     static constexpr int STAGE_BYTES = KSUB * SUB_BYTES;
+    static_assert(SUB_BYTES % 1024 == 0 && A_SUB_BYTES % 1024 == 0, "swizzle needs 1024-byte aligned tiles");
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t) + 1024;  // +align slack
 };
+
+// One pipeline stage of MMAs.  TAIL = this is the last k-tile and K is not a multiple of BK: TMA zero-filled k >= K in
+// both operands, and (+0)*(+0) added to a -0.0 accumulator would give +0.0; feeding -0.0 on the X side makes the
+// padded product -0.0, and c + (-0.0) == c for every c.  Kept out of the steady-state loop (template) on purpose.
+template <typename Cfg, bool TAIL>
+__device__ __forceinline__ void dmma_consume_stage(double (&acc)[Cfg::MI][Cfg::NI][2], uint32_t st, const uint32_t (&offA)[2][2],
+                                                   const uint32_t (&offB)[4], int k_stage0, int K, int t)
+{
+#pragma unroll
+    for (int sub = 0; sub < Cfg::KSUB; ++sub) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+            // address = stage base + one of 8 thread-constant swizzled offsets + a compile-time immediate
+            double a[Cfg::MI], b[Cfg::NI];
+#pragma unroll
+            for (int mi = 0; mi < Cfg::MI; ++mi)
+                a[mi] = lds_f64(st + offA[mi & 1][k4 & 1] + (sub * Cfg::SUB_BYTES + (mi >> 1) * 2048 + k4 * 512));
+#pragma unroll
+            for (int ni = 0; ni < Cfg::NI; ++ni)
+                b[ni] = lds_f64(st + offB[k4] + (sub * Cfg::SUB_BYTES + Cfg::A_SUB_BYTES + ni * 1024));
+            if constexpr (TAIL) {
+                if (k_stage0 + sub * 16 + k4 * 4 + t >= K) {
+#pragma unroll
+                    for (int ni = 0; ni < Cfg::NI; ++ni) b[ni] = -0.0;
+                }
+            }
+#pragma unroll
+            for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+}
 
 template <typename Cfg, bool ACC>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
@@ -106,6 +142,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                      double* __restrict__ D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m)
 {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, KSUB = Cfg::KSUB, STAGES = Cfg::STAGES;
+    constexpr int MI = Cfg::MI, NI = Cfg::NI;
     extern __shared__ unsigned char smem_raw[];
     // the 128B swizzle is a function of address bits 4..9: tile bases must be 1024-byte aligned
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,7 +165,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
     if (warp >= Cfg::CONSUMER_WARPS) {
         // ===================== producer warpgroup: one thread issues every TMA of the CTA =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Cfg::PRODUCER_REGS));
+        if constexpr (Cfg::REALLOC_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Cfg::PRODUCER_REGS));
         if (warp == Cfg::CONSUMER_WARPS && lane == 0) {
             tma_prefetch_desc(&mapA);
             tma_prefetch_desc(&mapX);
@@ -157,9 +194,9 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         return;
     }
 
-    // ===================== consumers: 2 warpgroups = 8 warps, 64 x 32 each =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Cfg::CONSUMER_REGS));
-    const int wm = warp & 1, wn = warp >> 1;
+    // ===================== consumers: WARPS_M x WARPS_N warps, (MI*8) x (NI*8) each =====================
+    if constexpr (Cfg::REALLOC_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Cfg::CONSUMER_REGS));
+    const int wm = warp % Cfg::WARPS_M, wn = warp / Cfg::WARPS_M;
     const int g = lane >> 2, t = lane & 3;
     // A fragment: physical row inside a 16-row box for MMA row g of sub-tile 0 (sub-tile 1 adds 4): chunk/half form
     const int a_chunk = ((g >> 1) & 1) * 4 + (g >> 2);  // logical 16-byte chunk (sub-tile 1: +2)
@@ -170,6 +207,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const int sg_c0 = 2 * ((2 * t) & 3) + ((2 * t) >> 2);
     const int sg_c1 = 2 * ((2 * t + 1) & 3) + ((2 * t + 1) >> 2);
     const int pi_g = (g & 1) + 8 * ((g >> 1) & 1) + 2 * (g >> 2);  // + 4*sub
+    const int wrow0 = wm * MI * 8, wcol0 = wn * NI * 8;            // warp origin inside the CTA tile
     // Thread-constant swizzled byte offsets; everything else in a fragment address is a compile-time immediate.
     //   A: row r = 4*k4 + t, chunk = (a_chunk | p<<1) ^ (r & 7) = a_chunk ^ t ^ (p<<1) ^ (q<<2),  p = mi&1, q = k4&1
     //   X: chunk = (2*k4 + (t>>1)) ^ sg(g)
@@ -179,10 +217,10 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     for (int p = 0; p < 2; ++p)
 #pragma unroll
         for (int q = 0; q < 2; ++q)
-            offA[p][q] = (uint32_t)((wm * 4) * 2048 + t * 128 + (((a_chunk ^ t) ^ (p << 1) ^ (q << 2)) << 4) + a_half * 8);
+            offA[p][q] = (uint32_t)((wrow0 / 16) * 2048 + t * 128 + (((a_chunk ^ t) ^ (p << 1) ^ (q << 2)) << 4) + a_half * 8);
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4)
-        offB[k4] = (uint32_t)((wn * 32 + sg_g) * 128 + (((k4 * 2 + (t >> 1)) ^ sg_g) << 4) + (t & 1) * 8);
+        offB[k4] = (uint32_t)((wcol0 + sg_g) * 128 + (((k4 * 2 + (t >> 1)) ^ sg_g) << 4) + (t & 1) * 8);
 
     const bool k_tail = (K % BK) != 0;
     int s = 0;
@@ -192,16 +230,16 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         raster(tile, tiles_m, tiles_n, group_m, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
 
-        double acc[8][4][2];
+        double acc[MI][NI][2];
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
+            for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     if constexpr (ACC) {
-                        int gm = m0 + wm * 64 + (mi >> 1) * 16 + pi_g + 4 * (mi & 1);
-                        int gn = n0 + wn * 32 + ni * 8 + (c ? sg_c1 : sg_c0);
+                        int gm = m0 + wrow0 + (mi >> 1) * 16 + pi_g + 4 * (mi & 1);
+                        int gn = n0 + wcol0 + ni * 8 + (c ? sg_c1 : sg_c0);
                         acc[mi][ni][c] = (gm < M && gn < N) ? D[(size_t)gn * ldd + gm] : 0.0;
                     } else {
                         acc[mi][ni][c] = -0.0;
@@ -211,30 +249,10 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         for (int kt = 0; kt < KT; ++kt) {
             mbar_wait(&full[s], phase);
             const uint32_t st = tiles_u32 + (uint32_t)s * Cfg::STAGE_BYTES;
-#pragma unroll
-            for (int sub = 0; sub < KSUB; ++sub) {
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    // address = stage base + one of 8 thread-constant swizzled offsets + a compile-time immediate
-                    double a[8], b[4];
-#pragma unroll
-                    for (int mi = 0; mi < 8; ++mi)
-                        a[mi] = lds_f64(st + offA[mi & 1][k4 & 1] + (sub * Cfg::SUB_BYTES + (mi >> 1) * 2048 + k4 * 512));
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni)
-                        b[ni] = lds_f64(st + offB[k4] + (sub * Cfg::SUB_BYTES + Cfg::A_SUB_BYTES + ni * 1024));
-                    // K tail: TMA zero-fills k >= K in both operands; (+0)*(+0) added to a -0.0 accumulator would give
-                    // +0.0.  Feeding -0.0 on the X side makes the padded product -0.0, and c + (-0.0) == c for every c.
-                    if (k_tail && kt == KT - 1 && (kt * BK + sub * 16 + k4 * 4 + t) >= K) {
-#pragma unroll
-                        for (int ni = 0; ni < 4; ++ni) b[ni] = -0.0;
-                    }
-#pragma unroll
-                    for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-                }
-            }
+            if (k_tail && kt == KT - 1)
+                dmma_consume_stage<Cfg, true>(acc, st, offA, offB, kt * BK, K, t);
+            else
+                dmma_consume_stage<Cfg, false>(acc, st, offA, offB, kt * BK, K, t);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             if (++s == STAGES) { s = 0; phase ^= 1; }
@@ -242,15 +260,15 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
         // ---- store (overwrite, column-major; src/gemm.jl:3-11), un-permuting rows/columns ----
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
+        for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const int gn = n0 + wn * 32 + ni * 8 + (c ? sg_c1 : sg_c0);
+                const int gn = n0 + wcol0 + ni * 8 + (c ? sg_c1 : sg_c0);
                 if (gn >= N) continue;
                 double* dcol = D + (size_t)gn * ldd;
 #pragma unroll
-                for (int mi = 0; mi < 8; ++mi) {
-                    const int gm = m0 + wm * 64 + (mi >> 1) * 16 + pi_g + 4 * (mi & 1);
+                for (int mi = 0; mi < MI; ++mi) {
+                    const int gm = m0 + wrow0 + (mi >> 1) * 16 + pi_g + 4 * (mi & 1);
                     if (gm < M) dcol[gm] = acc[mi][ni][c];
                 }
             }

@@ -56,9 +56,12 @@ def test_planner_is_pure_host_logic(jb):
     assert s["kernel"].startswith("simt_f64") and s["staging"] == "cp.async 16B"
     assert s["grid"] == (8192 // s["tile_m"]) * (8192 // s["tile_n"])  # one CTA per tile (non-persistent)
     assert jb.plan(8192, 8192, 8192, kernel=jb.F64_DMMA)["kernel"].startswith("dmma")
-    # ragged leading dimensions (M = 1023 doubles per column) cannot use 16-byte staging
+    # ragged leading dimensions (M = 1023 doubles per column) cannot use 16-byte staging directly: big products are
+    # re-aligned into scratch first and then take the TMA path, small ones use element-wise cp.async
     r = jb.plan(1023, 4097, 777)
-    assert r["staging"] == "cp.async element-wise" and r["grid"] >= 56
+    assert "re-aligning" in r["staging"] and r["kernel"].startswith("dmma_tma_f64") and 56 <= r["grid"] <= 148
+    small = jb.plan(129, 17, 127)
+    assert small["staging"] == "cp.async element-wise" and small["kernel"].startswith("dmma_f64")
     assert jb.plan(16384, 16384, 16384, "float32")["kernel"].startswith("simt_f32")
     names = jb.kernel_names()
     for i, n in enumerate(names):
