@@ -81,7 +81,8 @@ struct KernelInfo {
     size_t smem;
     float eff;           // measured throughput on many-wave shapes relative to the family's cp.async 128x128 kernel (sweep.json)
     bool needs_aligned;  // TMA kernels: 16-byte aligned bases and leading dimensions only
-    bool persistent;     // grid = min(tiles, #SMs), CTAs loop over the rasterised tile list
+    bool persistent;     // grid = min(tiles, #SMs * ctas_per_sm), CTAs loop over the rasterised tile list
+    int ctas_per_sm;     // resident CTAs per SM the kernel is built for (persistent kernels)
     LaunchFn launch[2][2];  // [aligned][acc]
     cudaError_t (*set_attr)();
 };
@@ -189,7 +190,7 @@ static int launch_dmma_tma(void* D, const void* A, const void* X, int M, int N, 
     if (int rc = make_tmap_2d(&mapA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 16, 16)) return rc;
     if (int rc = make_tmap_2d(&mapX, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, (uint64_t)K, (uint64_t)N, (uint64_t)ldx, 16, Cfg::BN)) return rc;
     int grid = tiles_m * tiles_n;
-    if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
+    if (grid > g_ctx.num_sms * Cfg::MIN_BLOCKS) grid = g_ctx.num_sms * Cfg::MIN_BLOCKS;
     gemm_dmma_tma_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mapA, mapX, (double*)D, M, N, K, ldd, tiles_m, tiles_n,
                                                                            group_m);
     return 0;
@@ -209,7 +210,7 @@ static cudaError_t attr_dmma_tma()
 
 #define SIMT_ENTRY(NAME, T, DT, CFG, EFF)                                                                          \
     {                                                                                                              \
-        NAME, DT, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF, false, false,    \
+        NAME, DT, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF, false, false, 1, \
             {{launch_simt<T, CFG, false, false>, launch_simt<T, CFG, false, true>},                                \
              {launch_simt<T, CFG, true, false>, launch_simt<T, CFG, true, true>}},                                 \
             attr_simt<T, CFG>                                                                                      \
@@ -217,7 +218,7 @@ static cudaError_t attr_dmma_tma()
 #define SIMT_F32X2_ENTRY(NAME, CFG, EFF)                                                                           \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F32, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
-            false, false,                                                                                          \
+            false, false, 1,                                                                                       \
             {{launch_simt_f32x2<CFG, false, false>, launch_simt_f32x2<CFG, false, true>},                          \
              {launch_simt_f32x2<CFG, true, false>, launch_simt_f32x2<CFG, true, true>}},                           \
             attr_simt_f32x2<CFG>                                                                                   \
@@ -225,7 +226,7 @@ static cudaError_t attr_dmma_tma()
 #define DMMA_ENTRY(NAME, CFG, EFF)                                                                                 \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F64, FAM_DMMA, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
-            false, false,                                                                                          \
+            false, false, 1,                                                                                       \
             {{launch_dmma<CFG, false, false>, launch_dmma<CFG, false, true>},                                      \
              {launch_dmma<CFG, true, false>, launch_dmma<CFG, true, true>}},                                       \
             attr_dmma<CFG>                                                                                         \
@@ -233,7 +234,7 @@ static cudaError_t attr_dmma_tma()
 #define DMMA_TMA_ENTRY(NAME, CFG, EFF)                                                                             \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F64, FAM_DMMA, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
-            true, true,                                                                                            \
+            true, true, CFG::MIN_BLOCKS,                                                                           \
             {{launch_needs_alignment, launch_needs_alignment}, {launch_dmma_tma<CFG, false>, launch_dmma_tma<CFG, true>}}, \
             attr_dmma_tma<CFG>                                                                                     \
     }
@@ -255,6 +256,9 @@ using T64_k32s3 = DmmaTmaCfg<2, 4, 8, 4, 2, 3>;      // 128x128, 3 stages of 64 
 using T64_128x64 = DmmaTmaCfg<2, 2, 8, 4, 2, 4>;     // 4 warps of 64x32, 4 stages of 48 KiB
 using T64_96x64 = DmmaTmaCfg<2, 2, 6, 4, 2, 4>;      // 4 warps of 48x32: tile count just under #SMs on ragged shapes
 using T64_64x64_k64 = DmmaTmaCfg<2, 2, 4, 4, 4, 3>;  // 4 warps of 32x32, BK = 64: tall-skinny (K = 64 is ONE stage)
+using T64_96x64_w8 = DmmaTmaCfg<2, 4, 6, 2, 2, 4>;   // 8 warps of 48x16: two warps per sub-partition hide latency
+using T64_64x64_x2 = DmmaTmaCfg<2, 2, 4, 4, 2, 3, 2>;  // 2 CTAs/SM (3 x 32 KiB each): epilogue of one overlaps the other
+using T64_128x64_w8 = DmmaTmaCfg<2, 4, 8, 2, 2, 4>;  // 8 warps of 64x16
 
 // NOTE: indices are part of the tuning interface (selector 100+i); append, do not reorder.
 static const KernelInfo g_kernels[] = {
@@ -276,6 +280,9 @@ static const KernelInfo g_kernels[] = {
     /* 15 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4", T64_128x64, 1.12f),
     /* 16 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4", T64_96x64, 1.08f),
     /* 17 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x64_s3", T64_64x64_k64, 1.00f),
+    /* 18 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4_w8", T64_96x64_w8, 1.09f),
+    /* 19 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.01f),
+    /* 20 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4_w8", T64_128x64_w8, 1.13f),
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
@@ -587,6 +594,14 @@ int jblas_b200_init(int device)
     CUDA_TRY(cudaEventCreate(&g_ctx.ev0));
     CUDA_TRY(cudaEventCreate(&g_ctx.ev1));
     CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_copy, cudaEventDisableTiming));
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;  // re-align scratch (cudaMallocAsync) stays cached across synchronisations
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     g_ctx.device = device;
     g_ctx.attrs_set = false;
     return set_all_attrs();
@@ -764,7 +779,8 @@ int jblas_b200_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t ldd, int
     const KernelInfo& k = g_kernels[p.kidx];
     out[0] = p.kidx; out[1] = k.bm; out[2] = k.bn; out[3] = k.bk; out[4] = k.stages; out[5] = k.threads;
     out[6] = (int64_t)p.tiles_m * p.tiles_n;
-    if (k.persistent && out[6] > (g_ctx.num_sms > 0 ? g_ctx.num_sms : 148)) out[6] = g_ctx.num_sms > 0 ? g_ctx.num_sms : 148;
+    const int64_t resident = (int64_t)(g_ctx.num_sms > 0 ? g_ctx.num_sms : 148) * k.ctas_per_sm;
+    if (k.persistent && out[6] > resident) out[6] = resident;
     out[7] = p.group_m; out[8] = (int64_t)k.smem; out[9] = realigned ? 2 : (p.aligned ? 1 : 0);
     return 0;
 }

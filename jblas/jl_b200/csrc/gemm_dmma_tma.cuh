@@ -86,14 +86,15 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map)
 }
 
 // CTA tile = (WARPS_M * MI * 8) x (WARPS_N * NI * 8); warp tile = MI x NI DMMA tiles (MI even: a 16-row box = 2 tiles).
-template <int WARPS_M_, int WARPS_N_, int MI_, int NI_, int KSUB_, int STAGES_>
+template <int WARPS_M_, int WARPS_N_, int MI_, int NI_, int KSUB_, int STAGES_, int MINB_ = 1>
 struct DmmaTmaCfg {
+    static constexpr int MIN_BLOCKS = MINB_;  // CTAs per SM: 2 lets one CTA's epilogue overlap the other's main loop
     static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, MI = MI_, NI = NI_;
     static constexpr int BM = WARPS_M * MI * 8, BN = WARPS_N * NI * 8, KSUB = KSUB_, BK = 16 * KSUB_, STAGES = STAGES_;
     static constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
     static_assert(MI % 2 == 0 && (CONSUMER_WARPS == 4 || CONSUMER_WARPS == 8) && BN <= 256, "unsupported tile");
     static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
-    static constexpr bool REALLOC_REGS = CONSUMER_WARPS == 8;  // 384 threads: 168 regs at launch -> 232 / 40
+    static constexpr bool REALLOC_REGS = CONSUMER_WARPS == 8 && MINB_ == 1;  // 384 threads: 168 regs at launch -> 232 / 40
     static constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;
     static constexpr int A_SUB_BYTES = BM * 128;  // BM/16 boxes x 2 KiB
     static constexpr int B_SUB_BYTES = BN * 128;  // 1 box
@@ -110,34 +111,39 @@ template <typename Cfg, bool TAIL>
 __device__ __forceinline__ void dmma_consume_stage(double (&acc)[Cfg::MI][Cfg::NI][2], uint32_t st, const uint32_t (&offA)[2][2],
                                                    const uint32_t (&offB)[4], int k_stage0, int K, int t)
 {
+    // Fragments are double-buffered in registers: the loads of step i+1 are issued before the MMAs of step i, so a
+    // warp that is alone on its SM sub-partition (4-warp tiles) does not expose the shared-memory latency.
+    // address = stage base + one of 8 thread-constant swizzled offsets + a compile-time immediate
+    constexpr int STEPS = Cfg::KSUB * 4;
+    double a[2][Cfg::MI], b[2][Cfg::NI];
+    auto load = [&](int step, int buf) {
+        const int sub = step >> 2, k4 = step & 3;
 #pragma unroll
-    for (int sub = 0; sub < Cfg::KSUB; ++sub) {
+        for (int mi = 0; mi < Cfg::MI; ++mi)
+            a[buf][mi] = lds_f64(st + offA[mi & 1][k4 & 1] + (sub * Cfg::SUB_BYTES + (mi >> 1) * 2048 + k4 * 512));
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-            // address = stage base + one of 8 thread-constant swizzled offsets + a compile-time immediate
-            double a[Cfg::MI], b[Cfg::NI];
+        for (int ni = 0; ni < Cfg::NI; ++ni)
+            b[buf][ni] = lds_f64(st + offB[k4] + (sub * Cfg::SUB_BYTES + Cfg::A_SUB_BYTES + ni * 1024));
+        if constexpr (TAIL) {
+            if (k_stage0 + step * 4 + t >= K) {
 #pragma unroll
-            for (int mi = 0; mi < Cfg::MI; ++mi)
-                a[mi] = lds_f64(st + offA[mi & 1][k4 & 1] + (sub * Cfg::SUB_BYTES + (mi >> 1) * 2048 + k4 * 512));
-#pragma unroll
-            for (int ni = 0; ni < Cfg::NI; ++ni)
-                b[ni] = lds_f64(st + offB[k4] + (sub * Cfg::SUB_BYTES + Cfg::A_SUB_BYTES + ni * 1024));
-            if constexpr (TAIL) {
-                if (k_stage0 + sub * 16 + k4 * 4 + t >= K) {
-#pragma unroll
-                    for (int ni = 0; ni < Cfg::NI; ++ni) b[ni] = -0.0;
-                }
+                for (int ni = 0; ni < Cfg::NI; ++ni) b[buf][ni] = -0.0;
             }
-#pragma unroll
-            for (int mi = 0; mi < Cfg::MI; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
+    };
+    load(0, 0);
+#pragma unroll
+    for (int step = 0; step < STEPS; ++step) {
+        if (step + 1 < STEPS) load(step + 1, (step + 1) & 1);
+#pragma unroll
+        for (int mi = 0; mi < Cfg::MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < Cfg::NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[step & 1][mi], b[step & 1][ni]);
     }
 }
 
 template <typename Cfg, bool ACC>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS)
 gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
                      double* __restrict__ D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m)
 {
