@@ -271,18 +271,18 @@ static const KernelInfo g_kernels[] = {
     /* 6 */ SIMT_ENTRY("simt_f32_128x128x16", float, JBLAS_B200_DT_F32, S32_128x128, 1.00f),
     /* 7 */ SIMT_ENTRY("simt_f32_128x64x16", float, JBLAS_B200_DT_F32, S32_128x64, 1.08f),
     /* 8 */ SIMT_ENTRY("simt_f32_64x64x16", float, JBLAS_B200_DT_F32, S32_64x64, 1.05f),
-    /* 9 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x16_s6", T64_k16s6, 1.17f),   // measured 35.84 vs 30.41 TFLOP/s (8192^3)
-    /* 10 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x32_s3", T64_k32s3, 1.19f),  // measured 36.32 TFLOP/s: the AUTO choice
+    /* 9 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x16_s6", T64_k16s6, 1.16f),   // 35.15-35.9 vs 30.2 TFLOP/s (8192^3, profiles/r1_sweep_*.json)
+    /* 10 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x32_s3", T64_k32s3, 1.20f),  // 36.1-36.3 TFLOP/s: the AUTO choice for big shapes
     /* 11 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x16", S32_128x128, 1.19f),
     /* 12 */ SIMT_F32X2_ENTRY("simt_f32x2_128x64x16", S32_128x64, 1.22f),
     /* 13 */ SIMT_F32X2_ENTRY("simt_f32x2_64x64x16", S32_64x64, 1.18f),
     /* 14 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x32", S32_128x128_k32, 1.28f),
-    /* 15 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4", T64_128x64, 1.12f),
-    /* 16 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4", T64_96x64, 1.08f),
-    /* 17 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x64_s3", T64_64x64_k64, 1.00f),
-    /* 18 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4_w8", T64_96x64_w8, 1.09f),
-    /* 19 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.01f),
-    /* 20 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4_w8", T64_128x64_w8, 1.13f),
+    /* 15 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4", T64_128x64, 1.02f),
+    /* 16 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4", T64_96x64, 0.99f),
+    /* 17 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x64_s3", T64_64x64_k64, 1.01f),
+    /* 18 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4_w8", T64_96x64_w8, 1.18f),
+    /* 19 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.18f),
+    /* 20 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4_w8", T64_128x64_w8, 1.195f),
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
