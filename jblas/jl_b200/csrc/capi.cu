@@ -18,6 +18,7 @@
 #include "gemm_dmma_tma.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_simt_f32x2.cuh"
+#include "gemm_tf32x3.cuh"
 
 using namespace jb;
 
@@ -68,7 +69,7 @@ static int require_init()
 // ---------------------------------------------------------------------------------------------------------
 // kernel registry
 // ---------------------------------------------------------------------------------------------------------
-enum Family { FAM_SIMT = 0, FAM_DMMA = 1 };
+enum Family { FAM_SIMT = 0, FAM_DMMA = 1, FAM_TF32X3 = 2 };
 
 typedef int (*LaunchFn)(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
                         int tiles_m, int tiles_n, int group_m, cudaStream_t s);
@@ -200,6 +201,43 @@ static int launch_needs_alignment(void*, const void*, const void*, int, int, int
 {
     return fail(JBLAS_B200_EUNSUPPORTED, "this kernel needs 16-byte aligned A/X bases and even leading dimensions (TMA)");
 }
+// 3xTF32: split A and X into (hi, lo) TF32 parts in stream-ordered scratch, then the tcgen05/TMEM kernel.
+template <typename Cfg, bool ACC>
+static int launch_tf32x3(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                         int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+{
+    const int64_t ldA2 = (M + 3) / 4 * 4, ldX2 = (K + 3) / 4 * 4;
+    float* parts = nullptr;  // [A_hi | A_lo | X_hi | X_lo]
+    const size_t nA = (size_t)ldA2 * K, nX = (size_t)ldX2 * N;
+    cudaError_t e = cudaMallocAsync((void**)&parts, (2 * nA + 2 * nX) * sizeof(float), s);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(JBLAS_B200_ENOMEM, "3xTF32 split scratch of %zu bytes: %s", (2 * nA + 2 * nX) * sizeof(float), cudaGetErrorString(e));
+    }
+    float *Ahi = parts, *Alo = parts + nA, *Xhi = parts + 2 * nA, *Xlo = parts + 2 * nA + nX;
+    split_tf32_kernel<<<dim3((unsigned)((M + 255) / 256), (unsigned)(K < 65535 ? K : 65535)), 256, 0, s>>>((const float*)A, lda, M, K, Ahi, Alo, ldA2);
+    split_tf32_kernel<<<dim3((unsigned)((K + 255) / 256), (unsigned)(N < 65535 ? N : 65535)), 256, 0, s>>>((const float*)X, ldx, K, N, Xhi, Xlo, ldX2);
+    g_launches += 2;
+    CUtensorMap mAh, mAl, mXh, mXl;
+    int rc = make_tmap_2d(&mAh, Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)K, (uint64_t)ldA2, 32, 32);
+    if (!rc) rc = make_tmap_2d(&mAl, Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)K, (uint64_t)ldA2, 32, 32);
+    if (!rc) rc = make_tmap_2d(&mXh, Xhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)N, (uint64_t)ldX2, 32, Cfg::BN);
+    if (!rc) rc = make_tmap_2d(&mXl, Xlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)N, (uint64_t)ldX2, 32, Cfg::BN);
+    if (!rc) {
+        int grid = tiles_m * tiles_n;
+        if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
+        gemm_tf32x3_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mAh, mAl, mXh, mXl, (float*)D, M, N, K, ldd, tiles_m, tiles_n, group_m);
+    }
+    cudaFreeAsync(parts, s);
+    return rc;
+}
+template <typename Cfg>
+static cudaError_t attr_tf32x3()
+{
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gemm_tf32x3_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+}
 template <typename Cfg>
 static cudaError_t attr_dmma_tma()
 {
@@ -231,6 +269,13 @@ static cudaError_t attr_dmma_tma()
              {launch_dmma<CFG, true, false>, launch_dmma<CFG, true, true>}},                                       \
             attr_dmma<CFG>                                                                                         \
     }
+#define TF32X3_ENTRY(NAME, CFG, EFF)                                                                               \
+    {                                                                                                              \
+        NAME, JBLAS_B200_DT_F32, FAM_TF32X3, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF, \
+            false, true, 1,                                                                                        \
+            {{launch_tf32x3<CFG, false>, launch_tf32x3<CFG, true>}, {launch_tf32x3<CFG, false>, launch_tf32x3<CFG, true>}}, \
+            attr_tf32x3<CFG>                                                                                       \
+    }
 #define DMMA_TMA_ENTRY(NAME, CFG, EFF)                                                                             \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F64, FAM_DMMA, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
@@ -259,6 +304,8 @@ using T64_64x64_k64 = DmmaTmaCfg<2, 2, 4, 4, 4, 3>;  // 4 warps of 32x32, BK = 6
 using T64_96x64_w8 = DmmaTmaCfg<2, 4, 6, 2, 2, 4>;   // 8 warps of 48x16: two warps per sub-partition hide latency
 using T64_64x64_x2 = DmmaTmaCfg<2, 2, 4, 4, 2, 3, 2>;  // 2 CTAs/SM (3 x 32 KiB each): epilogue of one overlaps the other
 using T64_128x64_w8 = DmmaTmaCfg<2, 4, 8, 2, 2, 4>;  // 8 warps of 64x16
+using X3_128x256 = Tf32x3Cfg<256, 2>;  // 2 stages of 96 KiB, two 256-column TMEM accumulators
+using X3_128x128 = Tf32x3Cfg<128, 3>;  // 3 stages of 64 KiB
 
 // NOTE: indices are part of the tuning interface (selector 100+i); append, do not reorder.
 static const KernelInfo g_kernels[] = {
@@ -283,6 +330,8 @@ static const KernelInfo g_kernels[] = {
     /* 18 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4_w8", T64_96x64_w8, 1.18f),
     /* 19 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.18f),
     /* 20 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4_w8", T64_128x64_w8, 1.195f),
+    /* 21 */ TF32X3_ENTRY("tf32x3_tcgen05_f32_128x256x32_s2", X3_128x256, 1.00f),
+    /* 22 */ TF32X3_ENTRY("tf32x3_tcgen05_f32_128x128x32_s3", X3_128x128, 0.80f),
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
@@ -316,8 +365,7 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
         else return fail(JBLAS_B200_EINVAL, "unknown Float64 kernel selector %d", selector);
     } else {
         if (selector == JBLAS_B200_F32_EXACT) family = FAM_SIMT;
-        else if (selector == JBLAS_B200_F32_3XTF32)
-            return fail(JBLAS_B200_EUNSUPPORTED, "3xTF32 tcgen05 path is not built in this version");
+        else if (selector == JBLAS_B200_F32_3XTF32) family = FAM_TF32X3;
         else return fail(JBLAS_B200_EINVAL, "unknown Float32 mode selector %d", selector);
     }
     const int vec = dtype == JBLAS_B200_DT_F64 ? 2 : 4;
