@@ -206,21 +206,24 @@ template <typename Cfg, bool ACC>
 static int launch_tf32x3(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
                          int tiles_m, int tiles_n, int group_m, cudaStream_t s)
 {
-    const int64_t ldA2 = (M + 3) / 4 * 4, ldX2 = (K + 3) / 4 * 4;
-    float* parts = nullptr;  // [A_hi | A_lo | X_hi | X_lo]
-    const size_t nA = (size_t)ldA2 * K, nX = (size_t)ldX2 * N;
+    const int64_t ldA2 = (K + 3) / 4 * 4, ldX2 = (K + 3) / 4 * 4;  // A is stored transposed: K contiguous, M columns
+    float* parts = nullptr;  // [A^T_hi | A^T_lo | X_hi | X_lo]
+    const size_t nA = (size_t)ldA2 * M, nX = (size_t)ldX2 * N;
     cudaError_t e = cudaMallocAsync((void**)&parts, (2 * nA + 2 * nX) * sizeof(float), s);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(JBLAS_B200_ENOMEM, "3xTF32 split scratch of %zu bytes: %s", (2 * nA + 2 * nX) * sizeof(float), cudaGetErrorString(e));
     }
     float *Ahi = parts, *Alo = parts + nA, *Xhi = parts + 2 * nA, *Xlo = parts + 2 * nA + nX;
-    split_tf32_kernel<<<dim3((unsigned)((M + 255) / 256), (unsigned)(K < 65535 ? K : 65535)), 256, 0, s>>>((const float*)A, lda, M, K, Ahi, Alo, ldA2);
+    {
+        unsigned gy = (unsigned)((K + 31) / 32);
+        split_tf32_transpose_kernel<<<dim3((unsigned)((M + 31) / 32), gy < 65535u ? gy : 65535u), dim3(32, 8), 0, s>>>((const float*)A, lda, M, K, Ahi, Alo, ldA2);
+    }
     split_tf32_kernel<<<dim3((unsigned)((K + 255) / 256), (unsigned)(N < 65535 ? N : 65535)), 256, 0, s>>>((const float*)X, ldx, K, N, Xhi, Xlo, ldX2);
     g_launches += 2;
     CUtensorMap mAh, mAl, mXh, mXl;
-    int rc = make_tmap_2d(&mAh, Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)K, (uint64_t)ldA2, 32, 32);
-    if (!rc) rc = make_tmap_2d(&mAl, Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)K, (uint64_t)ldA2, 32, 32);
+    int rc = make_tmap_2d(&mAh, Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)M, (uint64_t)ldA2, 32, Cfg::BM);
+    if (!rc) rc = make_tmap_2d(&mAl, Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)M, (uint64_t)ldA2, 32, Cfg::BM);
     if (!rc) rc = make_tmap_2d(&mXh, Xhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)N, (uint64_t)ldX2, 32, Cfg::BN);
     if (!rc) rc = make_tmap_2d(&mXl, Xlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)N, (uint64_t)ldX2, 32, Cfg::BN);
     if (!rc) {

@@ -10,8 +10,8 @@
 // accumulator:  lo*hi, hi*lo, hi*hi  (the lo*lo term, ~2^-22 relative, is dropped).  Credited flops stay 2*M*N*K.
 //
 // Kernel anatomy (256 threads, one CTA per SM, persistent over a rasterised tile list; tile = 128 x BN):
-//   warp 0 lane 0 : TMA producer -- 4 tensor maps (A_hi, A_lo as MN-major 32(m) x 32(k) boxes; X_hi, X_lo as K-major
-//                   32(k) x BN boxes), CU_TENSOR_MAP_SWIZZLE_128B, completes on full[s]
+//   warp 0 lane 0 : TMA producer -- 4 tensor maps (A^T_hi, A^T_lo as 32(k) x 128(m) boxes; X_hi, X_lo as 32(k) x BN
+//                   boxes; all K-major), CU_TENSOR_MAP_SWIZZLE_128B, completes on full[s]
 //   warp 1 lane 0 : MMA issuer   -- 3 x 4 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) per stage from
 //                   shared-memory descriptors; tcgen05.commit frees the stage (empty[s]) and publishes the
 //                   accumulator (tmem_full[a])
@@ -19,11 +19,11 @@
 //   warps 4..7    : epilogue     -- tcgen05.ld 32x32b.x32 (lane = row m, 32 consecutive columns n), coalesced column-
 //                   major stores (a warp writes 128 contiguous bytes per column), then tmem_empty[a]
 //
-// Shared-memory operand layouts are the canonical UMMA ones that TMA's 128B swizzle produces directly:
-//   A (M contiguous = "MN-major"): per 32-row m-chunk, BK k-rows of 128 B; 8 k-rows = one 1024-byte swizzle atom
-//                                  -> descriptor LBO = BK*128 B (next m-chunk), SBO = 1024 B (next 8 k), +1024 B per UMMA_K
-//   X (K contiguous = "K-major")  : BN rows (n) of 128 B (32 k); 8 rows = one atom
-//                                  -> descriptor SBO = 1024 B (next 8 n), +32 B per UMMA_K
+// Shared-memory operand layout = the canonical K-major UMMA layout that TMA's 128B swizzle produces directly:
+//   rows (m for A^T, n for X) of 128 B = 32 k; 8 rows = one 1024-byte swizzle atom
+//   -> descriptor SBO = 1024 B (next 8 rows), start address +32 B per UMMA_K (8 TF32)
+// A is column-major in HBM (M contiguous), which would be an "MN-major" operand; MN-major TF32 needs the special
+// 128B-swizzle/32B-atom layout, so the split pre-pass writes A TRANSPOSED instead (K contiguous) at no extra traffic.
 #pragma once
 #include <cuda.h>
 
@@ -48,6 +48,46 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t lds, in
         asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(rest));
         hi[(size_t)c * ld2 + r] = hf;
         lo[(size_t)c * ld2 + r] = __uint_as_float(l);
+    }
+}
+
+// Same split, but the output is TRANSPOSED: src is rows x cols (column-major, rows contiguous), hi/lo are written as
+// cols x rows (cols contiguous).  Used for A: MN-major TF32 operands need the special 128B/32B-atom layout, whereas a
+// K-major A^T uses exactly the same plain 128B-swizzle layout as X.  32x32 tiles through shared memory keep both the
+// global read (along rows) and the global writes (along cols) coalesced.
+__global__ void split_tf32_transpose_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols, float* __restrict__ hi,
+                                            float* __restrict__ lo, int64_t ld2)
+{
+    __shared__ float th[32][33], tl[32][33];
+    const int r0 = blockIdx.x * 32, tx = threadIdx.x, ty = threadIdx.y;  // block (32, 8)
+    for (int c0 = blockIdx.y * 32; c0 < cols; c0 += gridDim.y * 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + tx, c = c0 + ty + 8 * j;
+            float hf = 0.f, lf = 0.f;
+            if (r < rows && c < cols) {
+                const float a = src[(size_t)c * lds + r];
+                uint32_t h, l;
+                asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(a));
+                hf = __uint_as_float(h);
+                float rest = a - hf;
+                if (!isfinite(a)) rest = 0.f;
+                asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(rest));
+                lf = __uint_as_float(l);
+            }
+            th[ty + 8 * j][tx] = hf;  // [c][r]
+            tl[ty + 8 * j][tx] = lf;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + tx, r = r0 + ty + 8 * j;  // output element (c, r): c contiguous
+            if (r < rows && c < cols) {
+                hi[(size_t)r * ld2 + c] = th[tx][ty + 8 * j];
+                lo[(size_t)r * ld2 + c] = tl[tx][ty + 8 * j];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -116,8 +156,8 @@ struct Tf32x3Cfg {
     static constexpr int TMEM_COLS = 512;  // two accumulators of BN (<= 256) columns; power of two >= 32
     static_assert(BN % 32 == 0 && BN <= 256 && 2 * BN <= TMEM_COLS, "unsupported BN");
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
-    // instruction descriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), A MN-major (1<<15), B K-major, N>>3 at 17, M>>4 at 24
-    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // instruction descriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), A and B K-major (bits 15,16 = 0), N>>3 at 17, M>>4 at 24
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
 template <typename Cfg, bool ACC>
@@ -173,11 +213,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                     mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
                     unsigned char* st = tiles + (size_t)s * Cfg::STAGE_BYTES;
                     const int k0 = kt * BK;
-#pragma unroll
-                    for (int c = 0; c < BM / 32; ++c) {
-                        tma_load_2d(st + c * (BK * 128), &mapAhi, &full[s], m0 + c * 32, k0);
-                        tma_load_2d(st + Cfg::A_BYTES + c * (BK * 128), &mapAlo, &full[s], m0 + c * 32, k0);
-                    }
+                    tma_load_2d(st, &mapAhi, &full[s], k0, m0);
+                    tma_load_2d(st + Cfg::A_BYTES, &mapAlo, &full[s], k0, m0);
                     tma_load_2d(st + 2 * Cfg::A_BYTES, &mapXhi, &full[s], k0, n0);
                     tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapXlo, &full[s], k0, n0);
                     if (++s == STAGES) { s = 0; phase ^= 1; }
@@ -204,9 +241,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                     const uint32_t b_hi = st + 2 * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
-                        // A: next UMMA_K = next 8-k atom (+1024 B); X: next 8 k inside the 128-byte row (+32 B)
-                        const uint64_t dah = umma_smem_desc(a_hi + ks * 1024, BK * 128, 1024);
-                        const uint64_t dal = umma_smem_desc(a_lo + ks * 1024, BK * 128, 1024);
+                        // both operands K-major: next UMMA_K = next 8 k inside the 128-byte row (+32 B)
+                        const uint64_t dah = umma_smem_desc(a_hi + ks * 32, 16, 1024);
+                        const uint64_t dal = umma_smem_desc(a_lo + ks * 32, 16, 1024);
                         const uint64_t dbh = umma_smem_desc(b_hi + ks * 32, 16, 1024);
                         const uint64_t dbl = umma_smem_desc(b_lo + ks * 32, 16, 1024);
                         umma_tf32(d_tmem, dal, dbh, Cfg::IDESC, (kt | ks) ? 1u : 0u);  // small terms first
