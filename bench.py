@@ -223,9 +223,14 @@ def run_gpu(args):
         desc = f"Float64 jmul! column-sharded: M=K=8192, N=8192 per GPU x {world} GPUs, A broadcast from rank 0 in K panels"
     else:
         n_total, scaling = N, ("strong" if world > 1 else "weak")
-    selector = {"auto": None, "dmma": jb.F64_DMMA, "simt": jb.F64_SIMT}[args.kernel]
     if dtype == "float32":
-        selector = None
+        selector = {"auto": None, "simt": jb.F32_EXACT, "tf32x3": jb.F32_3XTF32}.get(args.kernel)
+        if args.kernel not in ("auto", "simt", "tf32x3"):
+            raise SystemExit("--kernel for a Float32 workload must be auto, simt or tf32x3")
+    else:
+        if args.kernel == "tf32x3":
+            raise SystemExit("--kernel tf32x3 needs a Float32 workload (--workload c3)")
+        selector = {"auto": None, "dmma": jb.F64_DMMA, "simt": jb.F64_SIMT}[args.kernel]
     sg = ShardedGemm(M, K, n_total, panel_k=args.panel_k, kernel=selector)
     A = jb.mrandn(M, K, dtype, seed=SEED_A) if rank == 0 else jb.empty_colmajor(M, K, dtype)
     X = jb.mrandn(K, sg.shard_cols, dtype, seed=SEED_X, first_col=sg.c0)
@@ -283,6 +288,12 @@ def run_gpu(args):
             ffma2, _ = jb.probe_pipe("ffma2_tile", 10000)
             peak, nominal = max(ffma, ffma2), FP32_NOMINAL_TFLOPS
             probe = {"ffma_chain_tflops": ffma, "ffma2_tile_tflops": ffma2}
+            if args.kernel == "tf32x3":
+                # 3 TF32 MMAs per credited FMA: the bound is the dense TF32 tensor peak / 3; MEASURED_PEAKS.json has a
+                # measured bf16 figure, TF32 runs at half the bf16 rate on this part (nominal 1.1 vs 2.25 PFLOP/s)
+                bf16 = float(peaks.get("bf16_tflops", 1590.0))
+                peak, nominal = bf16 / 2.0 / 3.0, 1125.0 / 3.0
+                probe = {"bf16_tflops_" + peak_src: bf16, "tf32_over_3": peak}
         per_launch_flops = flops_step / world / sg.launches_per_call()
         # kernel-only duration: time the local kernel launches alone on this stream (no collective)
         k0, k1 = sg.panels[0]
@@ -404,7 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "dmma", "simt"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "dmma", "simt", "tf32x3"])
     ap.add_argument("--panel-k", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
