@@ -320,7 +320,7 @@ def run_gpu(args):
         }
 
     # ---- e2e: the reference-facing call with HOST buffers (H2D of A and X, D2H of D inside the timed region) ----
-    e2e = run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_step, selector)
+    e2e = None if args.no_e2e else run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_step, selector)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -418,6 +418,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "dmma", "simt", "tf32x3"])
     ap.add_argument("--panel-k", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large workloads)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
