@@ -118,3 +118,64 @@ class ShardedGemm:
 
     def launches_per_call(self) -> int:
         return len(self.panels)
+
+    def from_host(self, D_host, A_host, X_host, D_shard, A, X_shard, nblocks: int = 4):
+        """End-to-end product on PINNED HOST shards (the host-facing form of the sharded mode).
+
+        `A_host` (K x M row-major = A column-major) matters on `root` only, `X_host` (cols x K) and `D_host`
+        (cols x M) are this rank's shards; `D_shard`, `A`, `X_shard` are the device buffers.  Three streams:
+          in   : root uploads A in K panels (each panel is broadcast as soon as it has landed), every rank uploads
+                 its X shard in `nblocks` column blocks (contiguous in column-major storage);
+          comm : the K-panel NCCL broadcasts of A;
+          main : once A is complete, column block b of D is multiplied (full K, one launch) as soon as X block b is
+                 there; `out` copies D block b back to the host while block b+1 is multiplied.
+        Every element's chain is a single-launch chain, so results equal __call__'s."""
+        import torch
+
+        if self.world == 1:
+            raise ValueError("from_host is the multi-rank path; use the C ABI host-pointer entry on one GPU")
+        dev = A.device
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=dev)
+        if getattr(self, "_in_stream", None) is None:
+            self._in_stream, self._out_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        main, comm, s_in, s_out = torch.cuda.current_stream(dev), self._comm_stream, self._in_stream, self._out_stream
+        for st in (comm, s_in, s_out):
+            st.wait_stream(main)  # previous users of the device buffers are done
+        At, Xt, Dt = A.t(), X_shard.t(), D_shard.t()  # row-major views: (K, M), (cols, K), (cols, M)
+        works = []
+        for k0, k1 in self.panels:
+            if self.rank == self.root:
+                with torch.cuda.stream(s_in):
+                    At[k0:k1].copy_(A_host[k0:k1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(s_in)
+                comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                works.append(self.dist.broadcast(At[k0:k1], src=self.root, group=self.group, async_op=True))
+        cols = self.shard_cols
+        nb = max(1, -(-cols // max(1, nblocks)))
+        blocks = [(c0, min(c0 + nb, cols)) for c0 in range(0, cols, nb)]
+        x_ready = []
+        with torch.cuda.stream(s_in):
+            for c0, c1 in blocks:
+                Xt[c0:c1].copy_(X_host[c0:c1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                x_ready.append(ev)
+        with torch.cuda.stream(comm):
+            for w in works:
+                w.wait()
+            a_ready = torch.cuda.Event()
+            a_ready.record(comm)
+        main.wait_event(a_ready)
+        for (c0, c1), ev in zip(blocks, x_ready):
+            main.wait_event(ev)
+            self.local_gemm(D_shard[:, c0:c1], A, X_shard[:, c0:c1], False, self.kernel)
+            done = torch.cuda.Event()
+            done.record(main)
+            s_out.wait_event(done)
+            with torch.cuda.stream(s_out):
+                D_host[c0:c1].copy_(Dt[c0:c1], non_blocking=True)
+        main.wait_stream(s_out)
+        return D_host

@@ -45,6 +45,20 @@ def _worker(rank, world, port, M, K, N, panel_k, out_dir):
             torch.cuda.synchronize()
             assert not torch.isnan(A).any() and not torch.isnan(D).any()
             res[tag] = D.cpu().numpy()
+            # host-facing pipelined form: pinned host shards in, pinned host shard out, same bits
+            Xh = torch.empty((sg.shard_cols, K), dtype=torch.float64).pin_memory()
+            Xh.copy_(X.t())
+            Dh = torch.full((sg.shard_cols, M), float("nan"), dtype=torch.float64).pin_memory()
+            Ah = None
+            if rank == 0:
+                Ah = torch.empty((K, M), dtype=torch.float64).pin_memory()
+                Ah.copy_(A.t())
+            A2 = jb.empty_colmajor(M, K, fill=float("nan"))
+            D2 = jb.empty_colmajor(M, sg.shard_cols, fill=float("nan"))
+            X2 = jb.empty_colmajor(K, sg.shard_cols, fill=float("nan"))
+            sg.from_host(Dh, Ah, Xh, D2, A2, X2, nblocks=3)
+            torch.cuda.synchronize()
+            assert np.array_equal(Dh.numpy().T, res[tag]), f"from_host differs from the device-resident path ({tag})"
             if tag == "simt":
                 np.save(os.path.join(out_dir, f"A{rank}.npy"), A.cpu().numpy())
                 np.save(os.path.join(out_dir, f"X{rank}.npy"), X.cpu().numpy())
