@@ -186,6 +186,12 @@ def load_peaks():
 
 
 def run_gpu(args):
+    # stdout must carry exactly ONE JSON line.  Libraries (NCCL's version banner, torchrun notices) printf() to fd 1,
+    # so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -193,19 +199,20 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
-        if world == 1 and args.gpus > 1:  # convenience: relaunch ourselves under torchrun
+        if world == 1 and args.gpus > 1:  # convenience: relaunch ourselves under torchrun (children get the real stdout)
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                    "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
-            return subprocess.call(cmd)
+            return subprocess.call(cmd, stdout=real_stdout)
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly ONE JSON line: NCCL printf()s a "NCCL version ..." banner to stdout at the VERSION and
+        # WARN debug levels, so those two are dropped (INFO and above go through NCCL's logger and are left alone)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
 
     from jblas.jl_b200 import build
@@ -339,7 +346,8 @@ def run_gpu(args):
                        "l2": f"inputs larger than L2: A+X+D = {(M * K + K * sg.shard_cols + M * sg.shard_cols) * es / 2**20:.0f} MiB per GPU vs 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -180,9 +180,9 @@ __global__ void __launch_bounds__(256) probe_ffma2_tile_kernel(float* out, int i
         for (int r = 0; r < 4; ++r) acc[j][r] = 0ull;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int r = 0; r < 4; ++r)  // the A pair is the reused operand, the broadcast scalar and the accumulator are fresh
 #pragma unroll
-            for (int r = 0; r < 4; ++r) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(acc[j][r]) : "l"(a[r]), "l"(b[j]));
+            for (int j = 0; j < 8; ++j) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(acc[j][r]) : "l"(a[r]), "l"(b[j]));
     }
     uint64_t s = 0;
 #pragma unroll

@@ -30,7 +30,9 @@ __device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi)
 }
 __device__ __forceinline__ void ffma2(uint64_t& d, uint64_t a, uint64_t b)
 {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(d) : "l"(a), "l"(b));
+    // volatile: keeps the issue order written below (A pair reused over 8 consecutive FFMA2); ptxas otherwise regroups
+    // the sequence around the broadcast scalar, which costs one more fresh register read per instruction
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(d) : "l"(a), "l"(b));
 }
 
 // Same tiling contract as SimtCfg<float,...>: warp 64 x 32, thread 8 x 8 (rows i*32 + tx*4 + v, cols j*4 + ty).
@@ -109,14 +111,20 @@ gemm_simt_f32x2_kernel(float* __restrict__ D, const float* __restrict__ A, const
                     ulonglong2 a[2];  // rows (0,1),(2,3) and (32,33),(34,35) of the thread, as packed pairs
 #pragma unroll
                     for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const ulonglong2*>(sA + (kc + kv) * LDA + i * 32);
+                    // (b, b) pairs fold into FFMA2's scalar-broadcast operand form (SASS `Rb.F32`), no MOVs are emitted.
+                    // Loop order: the A PAIR is the operand held in the reuse cache (8 consecutive FFMA2 share it), the
+                    // fresh operands per FFMA2 are one scalar + one accumulator pair = 3 registers instead of 4.
+                    uint64_t bb[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float bs = kv ? b[j].y : b[j].x;
-                        const uint64_t bb = pack_f32x2(bs, bs);
-                        ffma2(acc[j][0], a[0].x, bb);
-                        ffma2(acc[j][1], a[0].y, bb);
-                        ffma2(acc[j][2], a[1].x, bb);
-                        ffma2(acc[j][3], a[1].y, bb);
+                        bb[j] = pack_f32x2(bs, bs);
+                    }
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const uint64_t ap = (p & 1) ? a[p >> 1].y : a[p >> 1].x;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ffma2(acc[j][p], ap, bb[j]);
                     }
                 }
             }
@@ -125,14 +133,17 @@ gemm_simt_f32x2_kernel(float* __restrict__ D, const float* __restrict__ A, const
                 ulonglong2 a[2];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const ulonglong2*>(sA + k * LDA + i * 32);
+                uint64_t bb[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float bs = sB[j * 4 * LDB + k];
-                    const uint64_t bb = pack_f32x2(bs, bs);
-                    ffma2(acc[j][0], a[0].x, bb);
-                    ffma2(acc[j][1], a[0].y, bb);
-                    ffma2(acc[j][2], a[1].x, bb);
-                    ffma2(acc[j][3], a[1].y, bb);
+                    bb[j] = pack_f32x2(bs, bs);
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const uint64_t ap = (p & 1) ? a[p >> 1].y : a[p >> 1].x;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ffma2(acc[j][p], ap, bb[j]);
                 }
             }
         }
