@@ -103,6 +103,16 @@ int jblas_b200_gemm_f64_dev(double* D, const double* A, const double* X, int64_t
 int jblas_b200_gemm_f32_dev(float* D, const float* A, const float* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
                             int64_t lda, int64_t ldx, int accumulate, int mode, void* stream);
 
+/* ---- fastmul!-class BATCHED small products on device pointers ---------------------------
+ * `batch` independent products D_b = A_b * X_b in one launch; jBLAS names: D MxP, A MxN, X NxP, every matrix
+ * dense column-major, matrix b starts stride_* elements after matrix b-1.  The single-product fastmul!
+ * (src/kernels.jl:202-208) cannot amortise a GPU launch; this is its B200 form.  Same chain per element as jmul!
+ * (bit-identical to the reference arithmetic).  HBM-bound by design. */
+int jblas_b200_fastmul_batched_f64_dev(double* D, const double* A, const double* X, int64_t M, int64_t N, int64_t P,
+                                       int64_t batch, int64_t strideD, int64_t strideA, int64_t strideX, void* stream);
+int jblas_b200_fastmul_batched_f32_dev(float* D, const float* A, const float* X, int64_t M, int64_t N, int64_t P,
+                                       int64_t batch, int64_t strideD, int64_t strideA, int64_t strideX, void* stream);
+
 /* ---- device memory / transfers (the shim owns no caller memory; these are conveniences) ------------ */
 int jblas_b200_alloc(void** dptr, size_t bytes);
 int jblas_b200_free(void* dptr);

@@ -15,6 +15,9 @@ from .api import (  # noqa: F401
     JblasB200Error,
     Kernel,
     empty_colmajor,
+    empty_colmajor_batch,
+    fastmul_batched_,
+    mrandn_batch,
     fastmul_,
     gemm_,
     init,

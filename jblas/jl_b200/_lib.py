@@ -37,6 +37,8 @@ PROTOTYPES = {
     "jblas_b200_initkernel_f32": (c_int, _KERN),
     "jblas_b200_gemm_f64_dev": (c_int, _GEMM + [c_vp]),
     "jblas_b200_gemm_f32_dev": (c_int, _GEMM + [c_vp]),
+    "jblas_b200_fastmul_batched_f64_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
+    "jblas_b200_fastmul_batched_f32_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "jblas_b200_alloc": (c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
     "jblas_b200_free": (c_int, [c_vp]),
     "jblas_b200_h2d": (c_int, [c_vp, c_vp, ctypes.c_size_t]),

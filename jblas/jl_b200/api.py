@@ -227,6 +227,55 @@ def empty_colmajor(M: int, N: int, dtype="float64", device=None, fill=None):
     return store.t()
 
 
+def mrandn_batch(batch: int, M: int, N: int, dtype="float64", seed: int = 0x6A424C41, device=None):
+    """`batch` column-major M x N matrices of iid N(0,1) draws: shape (batch, M, N), strides (M*N, 1, M)."""
+    flat = mrandn(M * N, batch, dtype, seed, device)  # column b of the flat matrix is matrix b
+    return flat.t().reshape(batch, N, M).transpose(1, 2)
+
+
+def empty_colmajor_batch(batch: int, M: int, N: int, dtype="float64", device=None, fill=None):
+    import torch
+
+    dev = init(device if isinstance(device, int) else None)
+    tdt = {"float64": torch.float64, "float32": torch.float32}[str(dtype).replace("torch.", "")]
+    store = torch.empty((batch, N, M), dtype=tdt, device=f"cuda:{dev}")
+    if fill is not None:
+        store.fill_(fill)
+    return store.transpose(1, 2)
+
+
+def fastmul_batched_(D, A, X):
+    """Batched fastmul! (src/kernels.jl:202-208 is the single-product form): D[b] = A[b] * X[b] for every b in one launch.
+
+    D, A, X are torch CUDA tensors of shape (batch, M, P), (batch, M, N), (batch, N, P) whose matrices are dense
+    column-major (strides (s, 1, rows) with s >= rows*cols).  Exact chain per element (bit-identical to the oracle)."""
+    import torch
+
+    def desc(t, name):
+        if not _is_torch(t) or not t.is_cuda or t.dim() != 3:
+            raise ValueError(f"{name} must be a 3-D torch CUDA tensor (batch, rows, cols)")
+        if t.dtype not in (torch.float64, torch.float32):
+            raise TypeError(f"{name}: dtype {t.dtype} not supported")
+        b, r, c = t.shape
+        sb, sr, sc = t.stride()
+        if (r > 1 and sr != 1) or (c > 1 and sc != r):
+            raise ValueError(f"{name}: every matrix must be dense column-major (strides (s, 1, rows)), got {t.stride()}")
+        return b, r, c, (sb if b > 1 else r * c)
+
+    bD, M, P, sD = desc(D, "D")
+    bA, M2, N, sA = desc(A, "A")
+    bX, N2, P2, sX = desc(X, "X")
+    if not (D.dtype == A.dtype == X.dtype):
+        raise TypeError("D, A and X must share one element type")
+    if not (bD == bA == bX) or M2 != M or N2 != N or P2 != P:
+        raise ValueError(f"shape mismatch: D {tuple(D.shape)}, A {tuple(A.shape)}, X {tuple(X.shape)}")
+    init()
+    L = _lib.lib()
+    fn = L.jblas_b200_fastmul_batched_f64_dev if D.dtype == torch.float64 else L.jblas_b200_fastmul_batched_f32_dev
+    check(fn(D.data_ptr(), A.data_ptr(), X.data_ptr(), M, N, P, bD, sD, sA, sX, torch.cuda.current_stream(D.device).cuda_stream))
+    return D
+
+
 def plan(M: int, K: int, N: int, dtype="float64", kernel: int | None = None, ldd=None, lda=None, ldx=None) -> dict:
     """What the planner would launch for D(MxN) = A(MxK)*X(KxN): the B200 analogue of pick_kernel_size
     (src/kernel_structure.jl:76-99) and blocking_structure (src/memory_management.jl:78-140).  Pure host logic."""

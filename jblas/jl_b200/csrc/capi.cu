@@ -14,6 +14,7 @@
 #include <string>
 
 #include "aux_kernels.cuh"
+#include "fastmul_batched.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_dmma_tma.cuh"
 #include "gemm_simt.cuh"
@@ -743,6 +744,61 @@ int jblas_b200_initkernel_f32(float* pD, const float* pA, const float* pX, int64
                               int64_t stride_X, int64_t N)
 {
     return gemm_host<float>(JBLAS_B200_DT_F32, pD, pA, pX, Mk, N, Pk, stride_AD, stride_AD, stride_X, 0, JBLAS_B200_F32_EXACT);
+}
+
+}  // extern "C" (templates cannot have C linkage)
+
+// fastmul!-class batched small products, device pointers, jBLAS dimension names (D MxP, A MxN, X NxP).
+template <typename T>
+static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t N, int64_t P, int64_t batch, int64_t strideD,
+                               int64_t strideA, int64_t strideX, cudaStream_t s)
+{
+    if (int rc = require_init()) return rc;
+    if (M < 0 || N < 0 || P < 0 || batch < 0) return fail(JBLAS_B200_EINVAL, "negative dimension");
+    if (batch == 0 || M == 0 || P == 0) return 0;
+    if (N == 0) return fail(JBLAS_B200_EINVAL, "empty contraction (N = 0) is not defined for fastmul_batched");
+    if (!D || !A || !X) return fail(JBLAS_B200_EINVAL, "NULL matrix pointer");
+    if (strideD < M * P || strideA < M * N || strideX < N * P) return fail(JBLAS_B200_EINVAL, "batch stride smaller than one matrix");
+    if (M > 4096 || N > 4096 || P > 4096) return fail(JBLAS_B200_EUNSUPPORTED, "fastmul_batched is for small matrices; use gemm");
+    const int xpitch = (int)(N | 1);  // odd column pitch: the column lanes of a warp hit distinct banks
+    const size_t slot = ((size_t)M * N + (size_t)xpitch * P) * sizeof(T);
+    if (2 * slot > (size_t)200 * 1024)
+        return fail(JBLAS_B200_EUNSUPPORTED, "one product needs %zu bytes of shared memory; fastmul_batched is for small matrices, use gemm", slot);
+    const int bpp = (int)(((M + 1) / 2) * ((P + 1) / 2));
+    int G = bpp >= 256 ? 1 : 256 / bpp;                     // products multiplied side by side by one CTA
+    const size_t budget = (size_t)36 * 1024;                // per stage: keeps >= 3 CTAs per SM resident
+    while (G > 1 && G * slot > budget) --G;
+    if ((int64_t)G > batch) G = (int)batch;
+    const size_t smem = 2 * (size_t)G * slot;
+    static size_t attr_set[2] = {0, 0};
+    const int ti = sizeof(T) == 8 ? 0 : 1;
+    if (smem > 48 * 1024 && smem > attr_set[ti]) {
+        CUDA_TRY(cudaFuncSetAttribute(fastmul_batched_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+        attr_set[ti] = 220 * 1024;
+    }
+    int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 6) per_sm = 6;
+    const int64_t ngroups = (batch + G - 1) / G;
+    int64_t grid = (int64_t)g_ctx.num_sms * per_sm;
+    if (grid > ngroups) grid = ngroups;
+    fastmul_batched_kernel<T><<<(unsigned)grid, 256, smem, s>>>(D, A, X, (int)M, (int)N, (int)P, batch, strideD, strideA, strideX, G, xpitch);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int jblas_b200_fastmul_batched_f64_dev(double* D, const double* A, const double* X, int64_t M, int64_t N, int64_t P, int64_t batch,
+                                       int64_t strideD, int64_t strideA, int64_t strideX, void* stream)
+{
+    return fastmul_batched_dev<double>(D, A, X, M, N, P, batch, strideD, strideA, strideX, (cudaStream_t)stream);
+}
+int jblas_b200_fastmul_batched_f32_dev(float* D, const float* A, const float* X, int64_t M, int64_t N, int64_t P, int64_t batch,
+                                       int64_t strideD, int64_t strideA, int64_t strideX, void* stream)
+{
+    return fastmul_batched_dev<float>(D, A, X, M, N, P, batch, strideD, strideA, strideX, (cudaStream_t)stream);
 }
 
 int jblas_b200_alloc(void** dptr, size_t bytes)

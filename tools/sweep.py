@@ -68,6 +68,27 @@ def main():
         print(key, json.dumps(row), flush=True)
         del A, X, D, Dt
         torch.cuda.empty_cache()
+    # batched fastmul! (HBM-bound): algorithmic GB/s against the measured HBM peak, torch.bmm (cuBLAS batched) beside it
+    res["batched"] = {}
+    for dtype, M, N, P, batch in [("float64", 16, 32, 14, 1_000_000), ("float32", 16, 32, 14, 2_000_000), ("float64", 32, 32, 28, 400_000),
+                                  ("float64", 8, 8, 8, 4_000_000), ("float64", 64, 64, 64, 60_000)]:
+        key = f"batched_{dtype}_{M}x{N}x{P}_b{batch}"
+        if only and not any(o in key for o in only):
+            continue
+        es = 8 if dtype == "float64" else 4
+        A = jb.mrandn_batch(batch, M, N, dtype, seed=3)
+        X = jb.mrandn_batch(batch, N, P, dtype, seed=4)
+        D = jb.empty_colmajor_batch(batch, M, P, dtype)
+        nbytes = batch * (M * N + N * P + M * P) * es
+        flops = 2.0 * batch * M * N * P
+        ms = time_call(lambda: jb.fastmul_batched_(D, A, X), 5)
+        row = {"fastmul_batched": {"ms": ms, "GBps": nbytes / ms / 1e6, "tflops": flops / ms / 1e9}}
+        ms = time_call(lambda: torch.bmm(A, X), 5)
+        row["torch.bmm"] = {"ms": ms, "GBps": nbytes / ms / 1e6, "tflops": flops / ms / 1e9}
+        res["batched"][key] = row
+        print(key, json.dumps(row), flush=True)
+        del A, X, D
+        torch.cuda.empty_cache()
     with open(os.path.join(OUT, "sweep.json"), "w") as f:
         json.dump(res, f, indent=1)
 
