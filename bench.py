@@ -321,8 +321,14 @@ def run_gpu(args):
         achieved = per_launch_flops / (kms * 1e-3) / 1e12
         algo_bytes = (M * (k1 - k0) + (k1 - k0) * sg.shard_cols + M * sg.shard_cols) * es
         pl = jb.plan(M, k1 - k0, sg.shard_cols, dtype, kernel=selector)
+        traffic = None
+        try:  # DRAM bytes per launch of this kernel on this shape, from the committed ncu capture (if one exists)
+            tmap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tmap.get(f"{pl['kernel']}@{M}x{sg.shard_cols}x{k1 - k0}")
+        except Exception:
+            traffic = None
         roofline = {
-            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "kernel": pl["kernel"], "kernel_ms": kms, "flops_per_launch": per_launch_flops, "algorithmic_bytes_per_launch": algo_bytes,
             "peak_source": ("live register-only pipe probe in this run (MEASURED_PEAKS.json carries only HBM and bf16 figures): " + json.dumps(probe)),
             "frac_of_nominal": achieved / nominal, "nominal_peak": nominal,

@@ -30,19 +30,20 @@ fastmul_batched_kernel(T* __restrict__ D, const T* __restrict__ A, const T* __re
     const int mb = (M + 1) >> 1, pb = (P + 1) >> 1, bpp = mb * pb;  // 2x2 output blocks per product
     const int64_t ngroups = (batch + G - 1) / G;
 
+    // No integer divisions on the copy path: products are walked by warps, elements by lanes.
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     auto load_group = [&](int64_t grp, int stage) {
         T* st = smem + (size_t)stage * stage_elems;
         const int64_t p0 = grp * G;
         const int g_here = (int)min((int64_t)G, batch - p0);
-        // A parts: g_here * a_elems contiguous-per-product elements
-        for (int e = tid; e < g_here * a_elems; e += nthr) {
-            const int g = e / a_elems, i = e - g * a_elems;
-            cp_async_elem<T>(smem_u32(st + g * slot + i), A + (p0 + g) * strideA + i, true);
-        }
-        for (int e = tid; e < g_here * N * P; e += nthr) {
-            const int g = e / (N * P), i = e - g * (N * P);
-            const int c = i / N, k = i - c * N;
-            cp_async_elem<T>(smem_u32(st + g * slot + a_elems + c * xpitch + k), X + (p0 + g) * strideX + i, true);
+        for (int g = 0; g < g_here; ++g) {
+            const T* ga = A + (p0 + g) * strideA;
+            T* sa = st + g * slot;
+            for (int i = tid; i < a_elems; i += nthr) cp_async_elem<T>(smem_u32(sa + i), ga + i, true);
+            const T* gx = X + (p0 + g) * strideX;
+            T* sx = sa + a_elems;
+            for (int c = warp; c < P; c += nwarps)
+                for (int k = lane; k < N; k += 32) cp_async_elem<T>(smem_u32(sx + c * xpitch + k), gx + c * N + k, true);
         }
     };
 
