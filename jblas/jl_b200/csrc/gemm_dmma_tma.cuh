@@ -74,6 +74,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// Same, with an L2 eviction-priority hint (the 64-bit policy encodings createpolicy.fractional produces for fraction 1.0).
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull, kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ double lds_f64(uint32_t addr)
 {
     double v;
@@ -190,8 +200,12 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         const int k0 = kt * BK + sub * 16;
                         unsigned char* sa = st + sub * Cfg::SUB_BYTES;
 #pragma unroll
-                        for (int mo = 0; mo < BM / 16; ++mo) tma_load_2d(sa + mo * 2048, &mapA, &full[s], m0 + mo * 16, k0);
-                        tma_load_2d(sa + Cfg::A_SUB_BYTES, &mapX, &full[s], k0, n0);
+                        // The raster walks tile rows fastest inside a group of `group_m` rows, so consecutive waves of the
+                        // persistent grid re-use the SAME A row panels with NEW X column panels: keep A in L2 (evict last),
+                        // let X stream through (evict first).  Cuts DRAM re-reads; the kernel itself is tensor-pipe bound.
+                        for (int mo = 0; mo < BM / 16; ++mo)
+                            tma_load_2d_hint(sa + mo * 2048, &mapA, &full[s], m0 + mo * 16, k0, kL2EvictLast);
+                        tma_load_2d_hint(sa + Cfg::A_SUB_BYTES, &mapX, &full[s], k0, n0, kL2EvictFirst);
                     }
                     if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
