@@ -155,7 +155,8 @@ __device__ __forceinline__ void dmma_consume_stage(double (&acc)[Cfg::MI][Cfg::N
 template <typename Cfg, bool ACC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS)
 gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
-                     double* __restrict__ D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m)
+                     double* __restrict__ D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m,
+                     uint64_t l2_policy_a, uint64_t l2_policy_x)
 {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, KSUB = Cfg::KSUB, STAGES = Cfg::STAGES;
     constexpr int MI = Cfg::MI, NI = Cfg::NI;
@@ -200,12 +201,10 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         const int k0 = kt * BK + sub * 16;
                         unsigned char* sa = st + sub * Cfg::SUB_BYTES;
 #pragma unroll
-                        // The raster walks tile rows fastest inside a group of `group_m` rows, so consecutive waves of the
-                        // persistent grid re-use the SAME A row panels with NEW X column panels: keep A in L2 (evict last),
-                        // let X stream through (evict first).  Cuts DRAM re-reads; the kernel itself is tensor-pipe bound.
+                        // L2 eviction priorities per operand are chosen by the host (capi.cu: launch_dmma_tma).
                         for (int mo = 0; mo < BM / 16; ++mo)
-                            tma_load_2d_hint(sa + mo * 2048, &mapA, &full[s], m0 + mo * 16, k0, kL2EvictLast);
-                        tma_load_2d_hint(sa + Cfg::A_SUB_BYTES, &mapX, &full[s], k0, n0, kL2EvictFirst);
+                            tma_load_2d_hint(sa + mo * 2048, &mapA, &full[s], m0 + mo * 16, k0, l2_policy_a);
+                        tma_load_2d_hint(sa + Cfg::A_SUB_BYTES, &mapX, &full[s], k0, n0, l2_policy_x);
                     }
                     if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
