@@ -773,7 +773,7 @@ static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t 
     if (strideD < M * P || strideA < M * N || strideX < N * P) return fail(JBLAS_B200_EINVAL, "batch stride smaller than one matrix");
     if (M > 4096 || N > 4096 || P > 4096) return fail(JBLAS_B200_EUNSUPPORTED, "fastmul_batched is for small matrices; use gemm");
     const int xpitch = (int)(N | 1);  // odd column pitch: the column lanes of a warp hit distinct banks
-    const size_t slot = ((size_t)M * N + (size_t)xpitch * P) * sizeof(T);
+    const size_t slot = ((((size_t)M * N + (size_t)xpitch * P) + 1) & ~(size_t)1) * sizeof(T);  // even element count, as in the kernel
     if (2 * slot > (size_t)200 * 1024)
         return fail(JBLAS_B200_EUNSUPPORTED, "one product needs %zu bytes of shared memory; fastmul_batched is for small matrices, use gemm", slot);
     const int bpp = (int)(((M + 1) / 2) * ((P + 1) / 2));

@@ -24,7 +24,8 @@ fastmul_batched_kernel(T* __restrict__ D, const T* __restrict__ A, const T* __re
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
     const int a_elems = M * N, x_elems = xpitch * P;
-    const int slot = a_elems + x_elems;          // one product: A (M x N dense) then X (N x P, column pitch xpitch)
+    const int slot = (a_elems + x_elems + 1) & ~1;  // one product: A (M x N dense) then X (N x P, column pitch xpitch); even
+                                                    // element count keeps every A copy 2-element aligned for paired loads
     const int stage_elems = G * slot;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int mb = (M + 1) >> 1, pb = (P + 1) >> 1, bpp = mb * pb;  // 2x2 output blocks per product
@@ -32,10 +33,23 @@ fastmul_batched_kernel(T* __restrict__ D, const T* __restrict__ A, const T* __re
 
     // No integer divisions on the copy path: products are walked by warps, elements by lanes.
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const bool tiny = (a_elems < 256) || (N < 16);
     auto load_group = [&](int64_t grp, int stage) {
         T* st = smem + (size_t)stage * stage_elems;
         const int64_t p0 = grp * G;
         const int g_here = (int)min((int64_t)G, batch - p0);
+        if (tiny) {  // very small matrices: flat element loops keep every lane busy (the divisions are cheap next to HBM time)
+            for (int e = tid; e < g_here * a_elems; e += nthr) {
+                const int g = e / a_elems, i = e - g * a_elems;
+                cp_async_elem<T>(smem_u32(st + g * slot + i), A + (p0 + g) * strideA + i, true);
+            }
+            for (int e = tid; e < g_here * N * P; e += nthr) {
+                const int g = e / (N * P), i = e - g * (N * P);
+                const int c = i / N, k = i - c * N;
+                cp_async_elem<T>(smem_u32(st + g * slot + a_elems + c * xpitch + k), X + (p0 + g) * strideX + i, true);
+            }
+            return;
+        }
         for (int g = 0; g < g_here; ++g) {
             const T* ga = A + (p0 + g) * strideA;
             T* sa = st + g * slot;
@@ -68,14 +82,27 @@ fastmul_batched_kernel(T* __restrict__ D, const T* __restrict__ A, const T* __re
             const T* sa = st + g * slot;
             const T* sx = sa + a_elems;
             T d00 = T(-0.0), d10 = T(-0.0), d01 = T(-0.0), d11 = T(-0.0);  // fma(a, b, -0.0) == a*b: the plain first product
+            if ((M & 1) == 0) {  // rows (r0, r0+1) are one aligned pair: a single paired shared-memory load
+                struct alignas(2 * sizeof(T)) Pair { T lo, hi; };
 #pragma unroll 4
-            for (int k = 0; k < N; ++k) {
-                const T a0 = sa[k * M + r0], a1 = sa[k * M + r1];
-                const T x0 = sx[c0 * xpitch + k], x1 = sx[c1 * xpitch + k];
-                d00 = fma_t(a0, x0, d00);
-                d10 = fma_t(a1, x0, d10);
-                d01 = fma_t(a0, x1, d01);
-                d11 = fma_t(a1, x1, d11);
+                for (int k = 0; k < N; ++k) {
+                    const Pair a = *reinterpret_cast<const Pair*>(sa + k * M + r0);
+                    const T x0 = sx[c0 * xpitch + k], x1 = sx[c1 * xpitch + k];
+                    d00 = fma_t(a.lo, x0, d00);
+                    d10 = fma_t(a.hi, x0, d10);
+                    d01 = fma_t(a.lo, x1, d01);
+                    d11 = fma_t(a.hi, x1, d11);
+                }
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < N; ++k) {
+                    const T a0 = sa[k * M + r0], a1 = sa[k * M + r1];
+                    const T x0 = sx[c0 * xpitch + k], x1 = sx[c1 * xpitch + k];
+                    d00 = fma_t(a0, x0, d00);
+                    d10 = fma_t(a1, x0, d10);
+                    d01 = fma_t(a0, x1, d01);
+                    d11 = fma_t(a1, x1, d11);
+                }
             }
             T* dp = D + (p0 + g) * strideD;
             dp[(size_t)c0 * M + r0] = d00;
