@@ -574,14 +574,17 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
         if (kp < 256) kp = 256;
         if (kp > K) kp = K;
     }
-    // column blocks of the LAST panel (D2H overlap): up to 4 blocks of a multiple of 128 columns
+    // column blocks of the LAST panel (D2H overlap): up to 8 blocks of a multiple of 128 columns
     int64_t nb = N;
     if ((size_t)M * N * es > panel_bytes) {
-        nb = ((N + 3) / 4 + 127) / 128 * 128;
+        nb = ((N + 7) / 8 + 127) / 128 * 128;
         if (nb > N) nb = N;
     }
-    for (int64_t k0 = 0; k0 < K; k0 += kp) {
-        const int64_t kc = (K - k0 < kp) ? (K - k0) : kp;
+    // The FIRST panel is a quarter panel: the multiply starts after ~16 MiB instead of ~64 MiB have crossed PCIe.
+    const int64_t kfirst = (kp < K && kp >= 1024) ? kp / 4 : kp;
+    for (int64_t k0 = 0; k0 < K;) {
+        const int64_t kstep = (k0 == 0) ? kfirst : kp;
+        const int64_t kc = (K - k0 < kstep) ? (K - k0) : kstep;
         const bool last = (k0 + kc >= K);
         const int acc = (accumulate || k0 > 0) ? 1 : 0;
         CUDA_TRY(cudaMemcpy2DAsync(dA + k0 * dM, dM * es, A + k0 * lda, lda * es, M * es, kc, cudaMemcpyHostToDevice, cs));
@@ -601,6 +604,7 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
                 CUDA_TRY(cudaMemcpy2DAsync(D + n0 * ldd, ldd * es, dD + n0 * dM, dM * es, M * es, nc, cudaMemcpyDeviceToHost, cs));
             }
         }
+        k0 += kc;
     }
     if (K == 0) {
         CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
