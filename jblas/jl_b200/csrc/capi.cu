@@ -13,6 +13,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "aux_kernels.cuh"
 #include "fastmul_batched.cuh"
@@ -530,6 +531,32 @@ static int ensure_ws(int i, size_t bytes)
     return 0;
 }
 
+// Optional timeline of the host-pointer pipeline (JBLAS_B200_TRACE=1): one CUDA event per stage, printed to stderr.
+struct HostTrace {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> tag;
+    void mark(const char* what, int64_t idx, cudaStream_t st)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        tag.push_back(std::string(what) + " " + std::to_string(idx));
+    }
+    void dump(cudaEvent_t t0)
+    {
+        if (!on) return;
+        for (size_t i = 0; i < ev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t0, ev[i]);
+            fprintf(stderr, "[jblas_b200 trace] %8.3f ms  %s\n", ms, tag[i].c_str());
+            cudaEventDestroy(ev[i]);
+        }
+    }
+};
+
 // Synchronous host-pointer GEMM: the literal drop-in for jmul!(D, A, X).  Everything is pipelined over K PANELS:
 //   copy stream : for panel p:  A[:, kp] and X[kp, :]   (H2D; panel p+1 travels while panel p is multiplied)
 //   compute     : D (+)= A[:, kp] * X[kp, :]  with accumulate = (p > 0): ascending k per element, so the chain (and,
@@ -557,6 +584,8 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
     T* dA = (T*)g_ctx.ws[1];
     T* dX = (T*)g_ctx.ws[2];
     cudaStream_t cs = g_ctx.copy_stream, ks = g_ctx.stream;
+    HostTrace trace;
+    trace.on = getenv("JBLAS_B200_TRACE") != nullptr;
     CUDA_TRY(cudaEventRecord(g_ctx.ev0, cs));
     if (accumulate) CUDA_TRY(cudaMemcpy2DAsync(dD, dM * es, D, ldd * es, M * es, N, cudaMemcpyHostToDevice, cs));
     if (K == 0) {
@@ -588,20 +617,25 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
         const bool last = (k0 + kc >= K);
         const int acc = (accumulate || k0 > 0) ? 1 : 0;
         CUDA_TRY(cudaMemcpy2DAsync(dA + k0 * dM, dM * es, A + k0 * lda, lda * es, M * es, kc, cudaMemcpyHostToDevice, cs));
+        trace.mark("h2d A panel done, k0 =", k0, cs);
         CUDA_TRY(cudaMemcpy2DAsync(dX + k0, dK * es, X + k0, ldx * es, kc * es, N, cudaMemcpyHostToDevice, cs));
+        trace.mark("h2d X rows done, k0 =", k0, cs);
         CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
         CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
         if (!last) {
             if (int rc = gemm_dev<T>(dtype, dD, dA + k0 * dM, dX + k0, M, kc, N, dM, dM, dK, acc, selector, ks)) return rc;
+            trace.mark("gemm panel done, k0 =", k0, ks);
         } else {
             for (int64_t n0 = 0; n0 < N; n0 += nb) {
                 const int64_t nc = (N - n0 < nb) ? (N - n0) : nb;
                 if (int rc = gemm_dev<T>(dtype, dD + n0 * dM, dA + k0 * dM, dX + k0 + n0 * dK, M, kc, nc, dM, dM, dK, acc,
                                          selector, ks))
                     return rc;
+                trace.mark("gemm last-panel block done, n0 =", n0, ks);
                 CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
                 CUDA_TRY(cudaStreamWaitEvent(cs, g_ctx.ev_copy, 0));
                 CUDA_TRY(cudaMemcpy2DAsync(D + n0 * ldd, ldd * es, dD + n0 * dM, dM * es, M * es, nc, cudaMemcpyDeviceToHost, cs));
+                trace.mark("d2h block done, n0 =", n0, cs);
             }
         }
         k0 += kc;
@@ -615,6 +649,7 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
     CUDA_TRY(cudaStreamSynchronize(cs));
     CUDA_TRY(cudaStreamSynchronize(ks));
     cudaEventElapsedTime(&g_ctx.last_ms, g_ctx.ev0, g_ctx.ev1);
+    trace.dump(g_ctx.ev0);
     return 0;
 }
 
