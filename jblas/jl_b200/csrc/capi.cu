@@ -52,7 +52,8 @@ struct Context {
     int device = -1;
     int num_sms = 0;
     cudaStream_t stream = nullptr;       // compute
-    cudaStream_t copy_stream = nullptr;  // H2D/D2H for the host-pointer entry points
+    cudaStream_t copy_stream = nullptr;  // H2D for the host-pointer entry points
+    cudaStream_t d2h_stream = nullptr;   // D2H (its own stream: PCIe is full duplex, one stream would serialise the two)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
     void* ws[3] = {nullptr, nullptr, nullptr};  // device staging for D, A, X (host-pointer entry points)
     size_t ws_bytes[3] = {0, 0, 0};
@@ -557,12 +558,15 @@ struct HostTrace {
     }
 };
 
-// Synchronous host-pointer GEMM: the literal drop-in for jmul!(D, A, X).  Everything is pipelined over K PANELS:
-//   copy stream : for panel p:  A[:, kp] and X[kp, :]   (H2D; panel p+1 travels while panel p is multiplied)
-//   compute     : D (+)= A[:, kp] * X[kp, :]  with accumulate = (p > 0): ascending k per element, so the chain (and,
-//                 for the exact kernels, every bit) is that of a single launch (kernel! semantics, src/kernels.jl:226)
-//   last panel  : split by column blocks of D; block b goes back to the host (D2H) while block b+1 is computed
-// With pinned caller buffers (jblas_b200_host_register) PCIe and the tensor pipe overlap almost completely.
+// Synchronous host-pointer GEMM: the literal drop-in for jmul!(D, A, X).  PCIe (H2D ~55 GB/s, D2H ~52 GB/s, full duplex)
+// and the tensor pipe are overlapped with a two-phase schedule over the (K panel, column block) grid:
+//   phase 1 -- K-PANEL major over the FIRST half of the columns: for each panel p the copy stream uploads A[:, kp] and the
+//              matching rows of X for those columns, the compute stream does  D[:, :N1] (+)= A[:, kp] * X[kp, :N1]
+//              (accumulate = p > 0: ascending k per element, i.e. the chain -- and for every kernel here every bit -- of
+//              a single launch; kernel! semantics, src/kernels.jl:226).  H2D-bound, but the pipe already works.
+//   phase 2 -- A is now resident: the remaining columns go COLUMN-BLOCK major, one full-K launch per block, while the
+//              finished blocks (first the whole phase-1 half) travel back on a separate D2H stream.
+// Only the last block's D2H is exposed.  Small problems degenerate to one panel / one block.
 template <typename T>
 static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
                      int64_t ldx, int accumulate, int selector)
@@ -583,69 +587,70 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
     T* dD = (T*)g_ctx.ws[0];
     T* dA = (T*)g_ctx.ws[1];
     T* dX = (T*)g_ctx.ws[2];
-    cudaStream_t cs = g_ctx.copy_stream, ks = g_ctx.stream;
+    cudaStream_t cs = g_ctx.copy_stream, ks = g_ctx.stream, os = g_ctx.d2h_stream;
     HostTrace trace;
     trace.on = getenv("JBLAS_B200_TRACE") != nullptr;
     CUDA_TRY(cudaEventRecord(g_ctx.ev0, cs));
     if (accumulate) CUDA_TRY(cudaMemcpy2DAsync(dD, dM * es, D, ldd * es, M * es, N, cudaMemcpyHostToDevice, cs));
+    auto d2h = [&](int64_t n0, int64_t nc) -> int {  // compute stream -> D2H stream hand-over for columns [n0, n0+nc)
+        CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
+        CUDA_TRY(cudaStreamWaitEvent(os, g_ctx.ev_copy, 0));
+        CUDA_TRY(cudaMemcpy2DAsync(D + n0 * ldd, ldd * es, dD + n0 * dM, dM * es, M * es, nc, cudaMemcpyDeviceToHost, os));
+        trace.mark("d2h done, n0 =", n0, os);
+        return 0;
+    };
     if (K == 0) {
         CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
         CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
         if (int rc = gemm_dev<T>(dtype, dD, dA, dX, M, 0, N, dM, dM, 1, accumulate, selector, ks)) return rc;
-    }
-    // K panels: ~64 MiB of A (+ the matching rows of X) per panel -- big enough to amortise launches and keep the
-    // kernels efficient, small enough that the first multiply starts early
-    int64_t kp = K;
-    const size_t panel_bytes = (size_t)64 << 20;
-    if (K > 0 && (size_t)(M + N) * K * es > 2 * panel_bytes) {
-        kp = (int64_t)(panel_bytes / ((size_t)(M > N ? M : N) * es));
-        kp = kp / 64 * 64;
-        if (kp < 256) kp = 256;
-        if (kp > K) kp = K;
-    }
-    // column blocks of the LAST panel (D2H overlap): up to 8 blocks of a multiple of 128 columns
-    int64_t nb = N;
-    if ((size_t)M * N * es > panel_bytes) {
-        nb = ((N + 7) / 8 + 127) / 128 * 128;
-        if (nb > N) nb = N;
-    }
-    // The FIRST panel is a quarter panel: the multiply starts after ~16 MiB instead of ~64 MiB have crossed PCIe.
-    const int64_t kfirst = (kp < K && kp >= 1024) ? kp / 4 : kp;
-    for (int64_t k0 = 0; k0 < K;) {
-        const int64_t kstep = (k0 == 0) ? kfirst : kp;
-        const int64_t kc = (K - k0 < kstep) ? (K - k0) : kstep;
-        const bool last = (k0 + kc >= K);
-        const int acc = (accumulate || k0 > 0) ? 1 : 0;
-        CUDA_TRY(cudaMemcpy2DAsync(dA + k0 * dM, dM * es, A + k0 * lda, lda * es, M * es, kc, cudaMemcpyHostToDevice, cs));
-        trace.mark("h2d A panel done, k0 =", k0, cs);
-        CUDA_TRY(cudaMemcpy2DAsync(dX + k0, dK * es, X + k0, ldx * es, kc * es, N, cudaMemcpyHostToDevice, cs));
-        trace.mark("h2d X rows done, k0 =", k0, cs);
-        CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
-        CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
-        if (!last) {
-            if (int rc = gemm_dev<T>(dtype, dD, dA + k0 * dM, dX + k0, M, kc, N, dM, dM, dK, acc, selector, ks)) return rc;
-            trace.mark("gemm panel done, k0 =", k0, ks);
-        } else {
-            for (int64_t n0 = 0; n0 < N; n0 += nb) {
-                const int64_t nc = (N - n0 < nb) ? (N - n0) : nb;
-                if (int rc = gemm_dev<T>(dtype, dD + n0 * dM, dA + k0 * dM, dX + k0 + n0 * dK, M, kc, nc, dM, dM, dK, acc,
-                                         selector, ks))
-                    return rc;
-                trace.mark("gemm last-panel block done, n0 =", n0, ks);
-                CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
-                CUDA_TRY(cudaStreamWaitEvent(cs, g_ctx.ev_copy, 0));
-                CUDA_TRY(cudaMemcpy2DAsync(D + n0 * ldd, ldd * es, dD + n0 * dM, dM * es, M * es, nc, cudaMemcpyDeviceToHost, cs));
-                trace.mark("d2h block done, n0 =", n0, cs);
-            }
+        if (int rc = d2h(0, N)) return rc;
+    } else {
+        const size_t panel_bytes = (size_t)64 << 20;
+        const bool big = (size_t)(M + N) * K * es > 2 * panel_bytes;
+        // K panels of ~64 MiB of A; the first one is a quarter panel so the multiply starts early
+        int64_t kp = K;
+        if (big) {
+            kp = (int64_t)(panel_bytes / ((size_t)M * es));
+            kp = kp / 64 * 64;
+            if (kp < 256) kp = 256;
+            if (kp > K) kp = K;
         }
-        k0 += kc;
+        const int64_t kfirst = (kp < K && kp >= 1024) ? kp / 4 : kp;
+        // phase-1 columns: everything for small problems, otherwise the first half (multiple of 128)
+        int64_t N1 = N;
+        if (big && (size_t)M * N * es > panel_bytes && N >= 512) N1 = ((N / 2) + 127) / 128 * 128;
+        // phase-2 column blocks: ~64 MiB of D each
+        int64_t nb = (int64_t)(panel_bytes / ((size_t)M * es));
+        nb = nb / 128 * 128;
+        if (nb < 128) nb = 128;
+        for (int64_t k0 = 0; k0 < K;) {
+            const int64_t kstep = (k0 == 0) ? kfirst : kp;
+            const int64_t kc = (K - k0 < kstep) ? (K - k0) : kstep;
+            const int acc = (accumulate || k0 > 0) ? 1 : 0;
+            CUDA_TRY(cudaMemcpy2DAsync(dA + k0 * dM, dM * es, A + k0 * lda, lda * es, M * es, kc, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpy2DAsync(dX + k0, dK * es, X + k0, ldx * es, kc * es, N1, cudaMemcpyHostToDevice, cs));
+            trace.mark("h2d A panel + X rows (phase-1 columns) done, k0 =", k0, cs);
+            CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
+            CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
+            if (int rc = gemm_dev<T>(dtype, dD, dA + k0 * dM, dX + k0, M, kc, N1, dM, dM, dK, acc, selector, ks)) return rc;
+            trace.mark("gemm phase-1 panel done, k0 =", k0, ks);
+            k0 += kc;
+        }
+        if (int rc = d2h(0, N1)) return rc;
+        for (int64_t n0 = N1; n0 < N; n0 += nb) {
+            const int64_t nc = (N - n0 < nb) ? (N - n0) : nb;
+            CUDA_TRY(cudaMemcpy2DAsync(dX + n0 * dK, dK * es, X + n0 * ldx, ldx * es, K * es, nc, cudaMemcpyHostToDevice, cs));
+            trace.mark("h2d X column block done, n0 =", n0, cs);
+            CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
+            CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
+            if (int rc = gemm_dev<T>(dtype, dD + n0 * dM, dA, dX + n0 * dK, M, K, nc, dM, dM, dK, accumulate ? 1 : 0, selector, ks))
+                return rc;
+            trace.mark("gemm phase-2 block done, n0 =", n0, ks);
+            if (int rc = d2h(n0, nc)) return rc;
+        }
     }
-    if (K == 0) {
-        CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
-        CUDA_TRY(cudaStreamWaitEvent(cs, g_ctx.ev_copy, 0));
-        CUDA_TRY(cudaMemcpy2DAsync(D, ldd * es, dD, dM * es, M * es, N, cudaMemcpyDeviceToHost, cs));
-    }
-    CUDA_TRY(cudaEventRecord(g_ctx.ev1, cs));
+    CUDA_TRY(cudaEventRecord(g_ctx.ev1, os));
+    CUDA_TRY(cudaStreamSynchronize(os));
     CUDA_TRY(cudaStreamSynchronize(cs));
     CUDA_TRY(cudaStreamSynchronize(ks));
     cudaEventElapsedTime(&g_ctx.last_ms, g_ctx.ev0, g_ctx.ev1);
@@ -694,6 +699,7 @@ int jblas_b200_init(int device)
     g_ctx.num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.d2h_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&g_ctx.ev0));
     CUDA_TRY(cudaEventCreate(&g_ctx.ev1));
     CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_copy, cudaEventDisableTiming));
@@ -726,6 +732,7 @@ int jblas_b200_shutdown(void)
     if (g_ctx.ev_copy) cudaEventDestroy(g_ctx.ev_copy);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
+    if (g_ctx.d2h_stream) cudaStreamDestroy(g_ctx.d2h_stream);
     g_ctx = Context();
     return 0;
 }
