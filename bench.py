@@ -241,7 +241,7 @@ def run_gpu(args):
         if args.kernel == "tf32x3":
             raise SystemExit("--kernel tf32x3 needs a Float32 workload (--workload c3)")
         selector = {"auto": None, "dmma": jb.F64_DMMA, "simt": jb.F64_SIMT}[args.kernel]
-    sg = ShardedGemm(M, K, n_total, panel_k=args.panel_k, kernel=selector)
+    sg = ShardedGemm(M, K, n_total, panel_k=args.panel_k, kernel=selector, first_panel_k=args.first_panel_k or None)
     A = jb.mrandn(M, K, dtype, seed=SEED_A) if rank == 0 else jb.empty_colmajor(M, K, dtype)
     X = jb.mrandn(K, sg.shard_cols, dtype, seed=SEED_X, first_col=sg.c0)
     D = jb.empty_colmajor(M, sg.shard_cols, dtype, fill=float("nan"))
@@ -304,9 +304,9 @@ def run_gpu(args):
                 bf16 = float(peaks.get("bf16_tflops", 1590.0))
                 peak, nominal = bf16 / 2.0 / 3.0, 1125.0 / 3.0
                 probe = {"bf16_tflops_" + peak_src: bf16, "tf32_over_3": peak}
-        per_launch_flops = flops_step / world / sg.launches_per_call()
-        # kernel-only duration: time the local kernel launches alone on this stream (no collective)
-        k0, k1 = sg.panels[0]
+        # kernel-only duration: time the dominant local kernel launch (the largest K panel) alone on this stream
+        k0, k1 = max(sg.panels, key=lambda p: p[1] - p[0])
+        per_launch_flops = 2.0 * M * (k1 - k0) * sg.shard_cols
         ke0, ke1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = max(3, min(args.steps, 10))
         from jblas.jl_b200 import api
@@ -431,6 +431,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", default="auto", choices=["auto", "dmma", "simt", "tf32x3"])
     ap.add_argument("--panel-k", type=int, default=2048)
+    ap.add_argument("--first-panel-k", type=int, default=256, help="shorter first K panel of the A broadcast (0 = same as the others)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large workloads)")
     args = ap.parse_args()

@@ -27,13 +27,23 @@ def column_shard(n_cols: int, world: int, rank: int) -> tuple[int, int]:
     return c0, c0 + counts[rank]
 
 
-def k_panels(K: int, panel_k: int) -> list[tuple[int, int]]:
-    """K split into [k0, k1) panels of `panel_k` (multiple of 64 keeps 16-byte staging and full k-tiles)."""
+def k_panels(K: int, panel_k: int, first_k: int | None = None) -> list[tuple[int, int]]:
+    """K split into [k0, k1) panels of `panel_k` (multiple of 64 keeps 16-byte staging and full k-tiles).
+
+    `first_k` (multiple of 64, < panel_k) makes the FIRST panel shorter: the only broadcast that cannot hide behind a
+    multiply is the first one, so it should be small."""
     if panel_k <= 0:
         raise ValueError("panel_k must be positive")
-    if panel_k % 64:
-        raise ValueError("panel_k must be a multiple of 64")
-    return [(k0, min(k0 + panel_k, K)) for k0 in range(0, max(K, 0), panel_k)] or [(0, 0)]
+    if panel_k % 64 or (first_k is not None and (first_k <= 0 or first_k % 64)):
+        raise ValueError("panel sizes must be positive multiples of 64")
+    if K <= 0:
+        return [(0, 0)]
+    edges = [0]
+    if first_k is not None and first_k < panel_k and first_k < K:
+        edges.append(first_k)
+    while edges[-1] < K:
+        edges.append(min(edges[-1] + panel_k, K))
+    return list(zip(edges[:-1], edges[1:]))
 
 
 def _default_local_gemm(D, A, X, accumulate: bool, kernel):
@@ -52,7 +62,7 @@ class ShardedGemm:
     """
 
     def __init__(self, M: int, K: int, n_cols_total: int, group=None, root: int = 0, panel_k: int = 2048,
-                 kernel: Optional[int] = None, local_gemm: Optional[Callable] = None):
+                 kernel: Optional[int] = None, local_gemm: Optional[Callable] = None, first_panel_k: Optional[int] = None):
         import torch.distributed as dist
 
         self.dist = dist
@@ -62,7 +72,7 @@ class ShardedGemm:
         self.root = root
         self.M, self.K, self.n_total = M, K, n_cols_total
         self.c0, self.c1 = column_shard(n_cols_total, self.world, self.rank)
-        self.panels = k_panels(K, panel_k) if self.world > 1 else [(0, K)]
+        self.panels = k_panels(K, panel_k, first_panel_k) if self.world > 1 else [(0, K)]
         self.kernel = kernel
         self.local_gemm = local_gemm or _default_local_gemm
         self._comm_stream = None

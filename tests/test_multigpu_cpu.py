@@ -34,6 +34,8 @@ def test_k_panels():
     assert k_panels(8192, 2048) == [(0, 2048), (2048, 4096), (4096, 6144), (6144, 8192)]
     assert k_panels(100, 64) == [(0, 64), (64, 100)]
     assert k_panels(64, 2048) == [(0, 64)]
+    assert k_panels(8192, 2048, 256) == [(0, 256), (256, 2304), (2304, 4352), (4352, 6400), (6400, 8192)]
+    assert k_panels(200, 2048, 256) == [(0, 200)]
     with pytest.raises(ValueError):
         k_panels(100, 48)
 
