@@ -348,7 +348,7 @@ def run_gpu(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic N(0,1), device-generated Philox (mrandn analogue), seeds jBLA/jBLA+1",
             "config": {"workload": desc, "M": M, "K": K, "N_total": n_total, "N_per_gpu": sg.shard_cols, "kernel_selector": args.kernel,
-                       "parallelism": f"column-shard x{world}" + (f", A broadcast in {len(sg.panels)} K-panels of {args.panel_k}" if world > 1 else ""),
+                       "parallelism": f"column-shard x{world}" + (f", A broadcast in {len(sg.panels)} K-panels (first {sg.panels[0][1] - sg.panels[0][0]}, then {args.panel_k})" if world > 1 else ""),
                        "l2": f"inputs larger than L2: A+X+D = {(M * K + K * sg.shard_cols + M * sg.shard_cols) * es / 2**20:.0f} MiB per GPU vs 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
