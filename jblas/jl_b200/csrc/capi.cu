@@ -59,7 +59,12 @@ struct Context {
     size_t ws_bytes[3] = {0, 0, 0};
     float last_ms = 0.f;
     bool attrs_set = false;
+    int* tile_ctr = nullptr;  // kTileCtrSlots x {next tile, CTAs done}: work counters of the persistent TMA kernels, all zero at rest
 };
+// Each launch takes the next slot of the ring; a kernel leaves its slot zeroed (gemm_dmma_tma.cuh).  A slot could only be
+// shared by two live kernels if kTileCtrSlots launches were in flight at once, far beyond what the driver queues.
+static constexpr int kTileCtrSlots = 8192;
+static std::atomic<uint32_t> g_tile_ctr_seq{0};
 static Context g_ctx;
 static std::mutex g_mu;  // calls are serialised per context (SURVEY 8b "Threading")
 static std::atomic<int64_t> g_launches{0};
@@ -207,8 +212,14 @@ static int launch_dmma_tma(void* D, const void* A, const void* X, int M, int N, 
     if (hint_mode == 1) { pa = kL2EvictLast; px = kL2EvictFirst; }
     else if (hint_mode == 2) { pa = kL2EvictLast; px = kL2EvictNormal; }
     else if (hint_mode == 3) { pa = kL2EvictLast; px = kL2EvictLast; }
+    static int static_tiles = -1;
+    if (static_tiles < 0) {
+        const char* e = getenv("JBLAS_B200_STATIC_TILES");
+        static_tiles = (e && atoi(e)) ? 1 : 0;
+    }
+    int* ctr = static_tiles ? nullptr : g_ctx.tile_ctr + 2 * (g_tile_ctr_seq.fetch_add(1, std::memory_order_relaxed) % kTileCtrSlots);
     gemm_dmma_tma_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mapA, mapX, (double*)D, M, N, K, ldd, tiles_m, tiles_n,
-                                                                           group_m, pa, px);
+                                                                           group_m, pa, px, ctr);
     return 0;
 }
 static int launch_needs_alignment(void*, const void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, int, int,
@@ -322,6 +333,8 @@ using T64_64x64_k64 = DmmaTmaCfg<2, 2, 4, 4, 4, 3>;  // 4 warps of 32x32, BK = 6
 using T64_96x64_w8 = DmmaTmaCfg<2, 4, 6, 2, 2, 4>;   // 8 warps of 48x16: two warps per sub-partition hide latency
 using T64_64x64_x2 = DmmaTmaCfg<2, 2, 4, 4, 2, 3, 2>;  // 2 CTAs/SM (3 x 32 KiB each): epilogue of one overlaps the other
 using T64_128x64_w8 = DmmaTmaCfg<2, 4, 8, 2, 2, 4>;  // 8 warps of 64x16
+using T64_32x32_x2 = DmmaTmaCfg<2, 2, 2, 2, 4, 3, 2>;  // 4 warps of 16x16, 2 CTAs/SM: 256^3..512^3 fill the 148 SMs
+using T64_64x32_x2 = DmmaTmaCfg<2, 2, 4, 2, 2, 4, 2>;  // 4 warps of 32x16, 2 CTAs/SM
 using X3_128x256 = Tf32x3Cfg<256, 2>;  // 2 stages of 96 KiB, two 256-column TMEM accumulators
 using X3_128x128 = Tf32x3Cfg<128, 3>;  // 3 stages of 64 KiB
 
@@ -336,20 +349,22 @@ static const KernelInfo g_kernels[] = {
     /* 6 */ SIMT_ENTRY("simt_f32_128x128x16", float, JBLAS_B200_DT_F32, S32_128x128, 1.00f),
     /* 7 */ SIMT_ENTRY("simt_f32_128x64x16", float, JBLAS_B200_DT_F32, S32_128x64, 1.08f),
     /* 8 */ SIMT_ENTRY("simt_f32_64x64x16", float, JBLAS_B200_DT_F32, S32_64x64, 1.05f),
-    /* 9 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x16_s6", T64_k16s6, 1.16f),   // 35.15-35.9 vs 30.2 TFLOP/s (8192^3, profiles/r1_sweep_*.json)
+    /* 9 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x16_s6", T64_k16s6, 1.17f),   // 35.15-35.9 vs 30.2 TFLOP/s (8192^3, profiles/r1_sweep_*.json)
     /* 10 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x32_s3", T64_k32s3, 1.20f),  // 36.1-36.3 TFLOP/s: the AUTO choice for big shapes
     /* 11 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x16", S32_128x128, 1.19f),
     /* 12 */ SIMT_F32X2_ENTRY("simt_f32x2_128x64x16", S32_128x64, 1.22f),
     /* 13 */ SIMT_F32X2_ENTRY("simt_f32x2_64x64x16", S32_64x64, 1.18f),
     /* 14 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x32", S32_128x128_k32, 1.28f),
     /* 15 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4", T64_128x64, 1.02f),
-    /* 16 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4", T64_96x64, 0.99f),
+    /* 16 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4", T64_96x64, 1.01f),
     /* 17 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x64_s3", T64_64x64_k64, 1.01f),
-    /* 18 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4_w8", T64_96x64_w8, 1.18f),
-    /* 19 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.18f),
-    /* 20 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4_w8", T64_128x64_w8, 1.195f),
+    /* 18 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4_w8", T64_96x64_w8, 1.17f),
+    /* 19 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.175f),
+    /* 20 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4_w8", T64_128x64_w8, 1.185f),
     /* 21 */ TF32X3_ENTRY("tf32x3_tcgen05_f32_128x256x32_s2", X3_128x256, 1.00f),
     /* 22 */ TF32X3_ENTRY("tf32x3_tcgen05_f32_128x128x32_s3", X3_128x128, 0.80f),
+    /* 23 */ DMMA_TMA_ENTRY("dmma_tma_f64_32x32x64_s3_x2", T64_32x32_x2, 1.06f),
+    /* 24 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x32x32_s4_x2", T64_64x32_x2, 1.125f),
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
@@ -396,7 +411,15 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
         if (explicit_idx < 0 && k.needs_aligned && !out->aligned) continue;
         int64_t tiles = ((M + k.bm - 1) / k.bm) * ((N + k.bn - 1) / k.bn);
         double per_tile = (double)k.bm * k.bn;
-        double waves = (double)((tiles + num_sms - 1) / num_sms);
+        // rounds of resident CTAs; CTAs that share an SM (ctas_per_sm > 1) also share its pipes, so a round of c
+        // co-resident CTAs costs c tile-times once more than one of them actually lands on an SM
+        const int64_t resident = (int64_t)num_sms * k.ctas_per_sm;
+        const int64_t rounds = (tiles + resident - 1) / resident;
+        const int64_t last = tiles - (rounds - 1) * resident;                          // CTAs in the last round
+        const int64_t last_share = (last + num_sms - 1) / num_sms;                     // how many of them share an SM
+        // a CTA built to share its SM but left alone on it runs at ~0.8 of the shared rate (nothing overlaps its
+        // pipeline fill and epilogue): measured, profiles/r1_size_sweep_per_kernel.json
+        double waves = (double)((rounds - 1) * k.ctas_per_sm) + (last_share < k.ctas_per_sm ? 1.25 * last_share : (double)last_share);
         int warps = k.threads / 32;
         double t = waves * per_tile;
         double single = per_tile * 4.0 / (warps < 4 ? warps : 4);  // a lone CTA with <4 warps cannot fill an SM
@@ -637,8 +660,12 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
             k0 += kc;
         }
         if (int rc = d2h(0, N1)) return rc;
-        for (int64_t n0 = N1; n0 < N; n0 += nb) {
-            const int64_t nc = (N - n0 < nb) ? (N - n0) : nb;
+        // the last block's D2H is the one transfer nothing hides: split a short tail block off the final one
+        const int64_t tail = 256;
+        for (int64_t n0 = N1, nc = 0; n0 < N; n0 += nc) {
+            const int64_t left = N - n0;
+            nc = left < nb ? left : nb;
+            if (big && left <= nb && left >= 3 * tail) nc = left - tail;
             CUDA_TRY(cudaMemcpy2DAsync(dX + n0 * dK, dK * es, X + n0 * ldx, ldx * es, K * es, nc, cudaMemcpyHostToDevice, cs));
             trace.mark("h2d X column block done, n0 =", n0, cs);
             CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
@@ -703,6 +730,9 @@ int jblas_b200_init(int device)
     CUDA_TRY(cudaEventCreate(&g_ctx.ev0));
     CUDA_TRY(cudaEventCreate(&g_ctx.ev1));
     CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_copy, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc((void**)&g_ctx.tile_ctr, (size_t)kTileCtrSlots * 2 * sizeof(int)));
+    CUDA_TRY(cudaMemset(g_ctx.tile_ctr, 0, (size_t)kTileCtrSlots * 2 * sizeof(int)));
+    CUDA_TRY(cudaDeviceSynchronize());  // zero before any launch on the (non-blocking) library or caller streams
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -727,6 +757,7 @@ int jblas_b200_shutdown(void)
         g_ctx.ws[i] = nullptr;
         g_ctx.ws_bytes[i] = 0;
     }
+    if (g_ctx.tile_ctr) cudaFree(g_ctx.tile_ctr);
     if (g_ctx.ev0) cudaEventDestroy(g_ctx.ev0);
     if (g_ctx.ev1) cudaEventDestroy(g_ctx.ev1);
     if (g_ctx.ev_copy) cudaEventDestroy(g_ctx.ev_copy);

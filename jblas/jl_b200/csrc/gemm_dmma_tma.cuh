@@ -6,8 +6,13 @@
 //     shared-memory ring; no thread spends issue slots on copies;
 //   * the register-tile SIMD micro-kernel (src/gemm.jl:149-170, src/kernels.jl:212-275)  ->  mma.sync.m8n8k4.f64
 //     (SASS DMMA.8x8x4), MI x NI tiles per warp, accumulators in registers (FP64 has no tcgen05/TMEM kind);
-//   * the two tile loops of jmul! (src/gemm.jl:313)  ->  a persistent grid (one CTA per SM) walking a rasterised
-//     tile list, so the producer runs ahead across tile boundaries and the pipeline never drains.
+//   * the two tile loops of jmul! (src/gemm.jl:313)  ->  a persistent grid (one or two CTAs per SM) walking a rasterised
+//     tile list, so the producer runs ahead across tile boundaries and the pipeline never drains.  The list is handed
+//     out DYNAMICALLY: a CTA's first tile is blockIdx.x, every later one comes from a global atomic counter that the
+//     producer thread fetches one tile ahead and passes to the consumers through the pipeline stage (stage_tile[s]).
+//     A statically strided list leaves SMs idle in the last round (and, with two CTAs per SM, can put both long
+//     lists on one SM: 2048^3 ran at 8 tile-times instead of 7.25).  The counter pair resets itself: the last CTA to
+//     draw a past-the-end ticket zeroes it for the next launch that uses the slot (capi.cu hands out slots in a ring).
 //
 // Roles: WARPS_M x WARPS_N consumer warps (4 or 8 = 1 or 2 warpgroups) + one producer warpgroup whose first lane
 // issues every TMA of the CTA.  With 8 consumer warps, setmaxnreg moves the idle producer warpgroup's registers to the
@@ -111,7 +116,7 @@ struct DmmaTmaCfg {
     static constexpr int SUB_BYTES = A_SUB_BYTES + B_SUB_BYTES;
     static constexpr int STAGE_BYTES = KSUB * SUB_BYTES;
     static_assert(SUB_BYTES % 1024 == 0 && A_SUB_BYTES % 1024 == 0, "swizzle needs 1024-byte aligned tiles");
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t) + 1024;  // +align slack
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t) + STAGES * sizeof(int) + 1024;  // +align slack
 };
 
 // One pipeline stage of MMAs.  TAIL = this is the last k-tile and K is not a multiple of BK: TMA zero-filled k >= K in
@@ -156,7 +161,7 @@ template <typename Cfg, bool ACC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS)
 gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
                      double* __restrict__ D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m,
-                     uint64_t l2_policy_a, uint64_t l2_policy_x)
+                     uint64_t l2_policy_a, uint64_t l2_policy_x, int* __restrict__ tile_ctr)
 {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, KSUB = Cfg::KSUB, STAGES = Cfg::STAGES;
     constexpr int MI = Cfg::MI, NI = Cfg::NI;
@@ -165,6 +170,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty = full + STAGES;
+    volatile int* stage_tile = reinterpret_cast<volatile int*>(empty + STAGES);  // tile a stage belongs to; -1 = no more work
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -188,12 +194,17 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             tma_prefetch_desc(&mapX);
             int s = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int tile = blockIdx.x;  // grid <= num_tiles: every CTA owns at least this one
+            while (tile < num_tiles) {
+                // ticket for the NEXT tile, drawn now so the atomic's round trip hides behind this tile's k loop
+                // (tile_ctr == nullptr: static stride, kept for A/B measurements -- JBLAS_B200_STATIC_TILES=1)
+                const int next = tile_ctr ? atomicAdd(tile_ctr, 1) + (int)gridDim.x : tile + (int)gridDim.x;
                 int tm, tn;
                 raster(tile, tiles_m, tiles_n, group_m, tm, tn);
                 const int m0 = tm * BM, n0 = tn * BN;
                 for (int kt = 0; kt < KT; ++kt) {
                     mbar_wait(&empty[s], phase ^ 1);
+                    stage_tile[s] = tile;  // ordered before the consumers' read by the release-arrive below
                     mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
                     unsigned char* st = tiles + (size_t)s * Cfg::STAGE_BYTES;
 #pragma unroll
@@ -208,6 +219,16 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     }
                     if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
+                tile = next;
+            }
+            // end marker: one more stage that carries no data
+            mbar_wait(&empty[s], phase ^ 1);
+            stage_tile[s] = -1;
+            mbar_arrive(&full[s]);
+            // every CTA draws exactly one past-the-end ticket; whoever reports last knows nobody will draw again
+            if (tile_ctr && atomicAdd(tile_ctr + 1, 1) == (int)gridDim.x - 1) {
+                tile_ctr[0] = 0;
+                tile_ctr[1] = 0;
             }
         }
         return;
@@ -244,7 +265,10 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const bool k_tail = (K % BK) != 0;
     int s = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (;;) {
+        mbar_wait(&full[s], phase);  // first stage of the next tile (waited on again, trivially, at kt = 0)
+        const int tile = stage_tile[s];
+        if (tile < 0) break;
         int tm, tn;
         raster(tile, tiles_m, tiles_n, group_m, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;

@@ -238,6 +238,31 @@ def test_dmma_tma_kernels_even_strides_accumulate_edges(jb, shape):
         assert np.abs(got - want_acc).max() <= 2 * K * 2.0 ** -52 * (np.abs(Ad) @ np.abs(Xd) + np.abs(D0)).max()
 
 
+def test_dmma_tma_dynamic_tile_scheduler_many_tiles_repeated_and_concurrent(jb):
+    """The persistent TMA kernels draw tiles from a self-resetting global counter: many more tiles than resident CTAs,
+    back-to-back launches (the counter must be zero again each time) and launches in flight on two streams at once
+    (separate counter slots) must all give the single-launch chain result -- bit-identical to the exact SIMT kernel."""
+    import torch
+    from jblas.jl_b200 import api
+
+    M, K, N = 2080, 96, 1576  # 65 x 50 = 3250 tiles of 32x32, ragged in M and N
+    A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
+    dA, dX = to_dev(A), to_dev(X)
+    want = _run_dev(jb, A, X, jb.F64_SIMT)
+    assert bits_equal(want, oracle.oracle_gemm(A, X))
+    tma = [s for s in _dmma_selectors(jb) if "tma" in jb.kernel_names()[s - jb.EXPLICIT_BASE]]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for sel in tma:
+        outs = [to_dev(nan_f((M, N))) for _ in range(6)]
+        torch.cuda.synchronize()
+        for i, dD in enumerate(outs):  # alternate streams: consecutive launches overlap on the device
+            with torch.cuda.stream(s1 if i % 2 == 0 else s2):
+                api._gemm(dD, dA, dX, False, sel)
+        torch.cuda.synchronize()
+        for dD in outs:
+            assert bits_equal(to_host(dD), want), jb.kernel_names()[sel - jb.EXPLICIT_BASE]
+
+
 # ------------------------------------------------------------------------------------------------------
 # the reference-facing API: host pointers, kernel!/initkernel!/fastmul!, degenerate sizes
 # ------------------------------------------------------------------------------------------------------
