@@ -103,6 +103,32 @@ int jblas_b200_gemm_f64_dev(double* D, const double* A, const double* X, int64_t
 int jblas_b200_gemm_f32_dev(float* D, const float* A, const float* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
                             int64_t lda, int64_t ldx, int accumulate, int mode, void* stream);
 
+/* ---- the fused forms the reference planned ---------------------------------------------
+ * src/memory_management.jl:72-76: "add support for how many copies of each of the matrices we have, so that we can
+ * perform calculations such as  D = A*X + C  or  D = A*(X + C)  in one step" (the D_count/A_count/X_count keywords of
+ * blocking_structure, :78).  The reference never wrote them; defined here in its own chain arithmetic:
+ *   gemm_plus_c   : D = A*X + C, C is M x N.  Every element's chain STARTS from C[i,j] (d = C[i,j]; d = fma(A[i,k],
+ *                   X[k,j], d), k ascending) -- exactly kernel!'s accumulate (src/kernels.jl:226) with the start value
+ *                   read from C instead of D.  C may alias D (then it is kernel!); no extra pass over D.
+ *   gemm_x_plus_c : D = A*(X + C), C is K x N.  X + C is rounded once per element, then the jmul! chain.
+ * `_dev`: device pointers, asynchronous on `stream`.  Without `_dev`: host pointers, synchronous. */
+int jblas_b200_gemm_plus_c_f64_dev(double* D, const double* A, const double* X, const double* C, int64_t M, int64_t K,
+                                   int64_t N, int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int kernel, void* stream);
+int jblas_b200_gemm_plus_c_f32_dev(float* D, const float* A, const float* X, const float* C, int64_t M, int64_t K,
+                                   int64_t N, int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int mode, void* stream);
+int jblas_b200_gemm_x_plus_c_f64_dev(double* D, const double* A, const double* X, const double* C, int64_t M, int64_t K,
+                                     int64_t N, int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int kernel, void* stream);
+int jblas_b200_gemm_x_plus_c_f32_dev(float* D, const float* A, const float* X, const float* C, int64_t M, int64_t K,
+                                     int64_t N, int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int mode, void* stream);
+int jblas_b200_gemm_plus_c_f64(double* D, const double* A, const double* X, const double* C, int64_t M, int64_t K, int64_t N,
+                               int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int kernel);
+int jblas_b200_gemm_plus_c_f32(float* D, const float* A, const float* X, const float* C, int64_t M, int64_t K, int64_t N,
+                               int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int mode);
+int jblas_b200_gemm_x_plus_c_f64(double* D, const double* A, const double* X, const double* C, int64_t M, int64_t K, int64_t N,
+                                 int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int kernel);
+int jblas_b200_gemm_x_plus_c_f32(float* D, const float* A, const float* X, const float* C, int64_t M, int64_t K, int64_t N,
+                                 int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int mode);
+
 /* ---- fastmul!-class BATCHED small products on device pointers ---------------------------
  * `batch` independent products D_b = A_b * X_b in one launch; jBLAS names: D MxP, A MxN, X NxP, every matrix
  * dense column-major, matrix b starts stride_* elements after matrix b-1.  The single-product fastmul!

@@ -17,6 +17,8 @@ from .api import (  # noqa: F401
     empty_colmajor,
     empty_colmajor_batch,
     fastmul_batched_,
+    gemm_plus_c_,
+    gemm_x_plus_c_,
     mrandn_batch,
     fastmul_,
     gemm_,

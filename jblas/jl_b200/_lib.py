@@ -19,6 +19,7 @@ c_vp = ctypes.c_void_p
 _GEMM = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int]
 _JMUL = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64]
 _KERN = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64]
+_FUSED = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int]  # D, A, X, C, M, K, N, ldd, lda, ldx, ldc, sel
 PROTOTYPES = {
     "jblas_b200_init": (c_int, [c_int]),
     "jblas_b200_shutdown": (c_int, []),
@@ -37,6 +38,14 @@ PROTOTYPES = {
     "jblas_b200_initkernel_f32": (c_int, _KERN),
     "jblas_b200_gemm_f64_dev": (c_int, _GEMM + [c_vp]),
     "jblas_b200_gemm_f32_dev": (c_int, _GEMM + [c_vp]),
+    "jblas_b200_gemm_plus_c_f64_dev": (c_int, _FUSED + [c_vp]),
+    "jblas_b200_gemm_plus_c_f32_dev": (c_int, _FUSED + [c_vp]),
+    "jblas_b200_gemm_x_plus_c_f64_dev": (c_int, _FUSED + [c_vp]),
+    "jblas_b200_gemm_x_plus_c_f32_dev": (c_int, _FUSED + [c_vp]),
+    "jblas_b200_gemm_plus_c_f64": (c_int, _FUSED),
+    "jblas_b200_gemm_plus_c_f32": (c_int, _FUSED),
+    "jblas_b200_gemm_x_plus_c_f64": (c_int, _FUSED),
+    "jblas_b200_gemm_x_plus_c_f32": (c_int, _FUSED),
     "jblas_b200_fastmul_batched_f64_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "jblas_b200_fastmul_batched_f32_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "jblas_b200_alloc": (c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),

@@ -140,6 +140,47 @@ def jmul_(D, A, X, Aprefetch=7, Xprefetch=7, A_loc=3, X_loc=3, D_loc=3, *, kerne
 gemm_ = jmul_  # BASELINE.json calls the same entry `gemm!`
 
 
+def _fused(D, A, X, C, x_plus_c: bool, selector: int | None):
+    pD, M, N, ldd, tD, devD = _describe(D, "D")
+    pA, M2, K, lda, tA, devA = _describe(A, "A")
+    pX, K2, N2, ldx, tX, devX = _describe(X, "X")
+    pC, Cr, Cc, ldc, tC, devC = _describe(C, "C")
+    if not (tD == tA == tX == tC):
+        raise TypeError("D, A, X and C must share one element type")
+    want_c = (K, N) if x_plus_c else (M, N)
+    if M2 != M or K2 != K or N2 != N or (Cr, Cc) != want_c:
+        raise ValueError(f"dimension mismatch: D is {M}x{N}, A is {M2}x{K}, X is {K2}x{N2}, C is {Cr}x{Cc} (expected {want_c[0]}x{want_c[1]})")
+    if not (devD == devA == devX == devC):
+        raise ValueError("D, A, X and C must all be host arrays or all be GPU tensors")
+    if not devD and not D.flags.writeable:
+        raise ValueError("D must be writeable")
+    init()
+    L = _lib.lib()
+    if selector is None:
+        selector = F64_AUTO if tD == DT_F64 else F32_EXACT
+    name = "jblas_b200_gemm_" + ("x_plus_c" if x_plus_c else "plus_c") + ("_f64" if tD == DT_F64 else "_f32")
+    if devD:
+        import torch
+
+        stream = torch.cuda.current_stream(D.device).cuda_stream
+        check(getattr(L, name + "_dev")(pD, pA, pX, pC, M, K, N, ldd, lda, max(ldx, 1), max(ldc, 1), int(selector), stream))
+    else:
+        check(getattr(L, name)(pD, pA, pX, pC, M, K, N, ldd, lda, max(ldx, 1), max(ldc, 1), int(selector)))
+    return D
+
+
+def gemm_plus_c_(D, A, X, C, *, kernel: int | None = None):
+    """D = A*X + C, the first fused form the reference planned (src/memory_management.jl:72-76).  Each element's fma
+    chain starts from C[i,j] -- kernel!'s accumulate (src/kernels.jl:226) reading its start value from C; C may be D."""
+    return _fused(D, A, X, C, False, kernel)
+
+
+def gemm_x_plus_c_(D, A, X, C, *, kernel: int | None = None):
+    """D = A*(X + C), the second planned fused form (src/memory_management.jl:72-76); C is K x N like X.  X + C is
+    rounded once per element, then the jmul! chain."""
+    return _fused(D, A, X, C, True, kernel)
+
+
 def fastmul_(D, A, X):
     """fastmul!(D, A, X) (src/kernels.jl:202-208): D = A*X for small matrices, any row count (the reference masks
     the row remainder, src/kernels.jl:59-75).  Runs the exact (bit-identical chain) kernels."""

@@ -80,8 +80,9 @@ static int require_init()
 // ---------------------------------------------------------------------------------------------------------
 enum Family { FAM_SIMT = 0, FAM_DMMA = 1, FAM_TF32X3 = 2 };
 
+// Cin/ldc: the matrix an accumulating launch starts from (== D for D += A*X; another matrix for D = A*X + C); unused otherwise
 typedef int (*LaunchFn)(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
-                        int tiles_m, int tiles_n, int group_m, cudaStream_t s);
+                        int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc);
 
 struct KernelInfo {
     const char* name;
@@ -95,14 +96,25 @@ struct KernelInfo {
     int ctas_per_sm;     // resident CTAs per SM the kernel is built for (persistent kernels)
     LaunchFn launch[2][2];  // [aligned][acc]
     cudaError_t (*set_attr)();
+    int (*query_occ)();  // non-persistent kernels: CTAs of the aligned variant the hardware keeps resident per SM
 };
+template <typename K>
+static int occupancy_of(K kernel, int threads, size_t smem)
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
 
 template <typename T, typename Cfg, bool ALIGNED, bool ACC>
 static int launch_simt(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
-                       int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+                       int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
 {
     gemm_simt_kernel<T, Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
-        (T*)D, (const T*)A, (const T*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m);
+        (T*)D, (const T*)A, (const T*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m, (const T*)Cin, ldc);
     return 0;
 }
 template <typename T, typename Cfg>
@@ -119,10 +131,10 @@ static cudaError_t attr_simt()
 }
 template <typename Cfg, bool ALIGNED, bool ACC>
 static int launch_simt_f32x2(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
-                             int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+                             int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
 {
     gemm_simt_f32x2_kernel<Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
-        (float*)D, (const float*)A, (const float*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m);
+        (float*)D, (const float*)A, (const float*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m, (const float*)Cin, ldc);
     return 0;
 }
 template <typename Cfg>
@@ -139,10 +151,10 @@ static cudaError_t attr_simt_f32x2()
 }
 template <typename Cfg, bool ALIGNED, bool ACC>
 static int launch_dmma(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
-                       int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+                       int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
 {
     gemm_dmma_kernel<Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
-        (double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m);
+        (double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m, (const double*)Cin, ldc);
     return 0;
 }
 template <typename Cfg>
@@ -194,7 +206,7 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType 
 
 template <typename Cfg, bool ACC>
 static int launch_dmma_tma(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
-                           int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+                           int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
 {
     CUtensorMap mapA, mapX;
     if (int rc = make_tmap_2d(&mapA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 16, 16)) return rc;
@@ -219,18 +231,18 @@ static int launch_dmma_tma(void* D, const void* A, const void* X, int M, int N, 
     }
     int* ctr = static_tiles ? nullptr : g_ctx.tile_ctr + 2 * (g_tile_ctr_seq.fetch_add(1, std::memory_order_relaxed) % kTileCtrSlots);
     gemm_dmma_tma_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mapA, mapX, (double*)D, M, N, K, ldd, tiles_m, tiles_n,
-                                                                           group_m, pa, px, ctr);
+                                                                           group_m, pa, px, ctr, (const double*)Cin, ldc);
     return 0;
 }
 static int launch_needs_alignment(void*, const void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, int, int,
-                                  cudaStream_t)
+                                  cudaStream_t, const void*, int64_t)
 {
     return fail(JBLAS_B200_EUNSUPPORTED, "this kernel needs 16-byte aligned A/X bases and even leading dimensions (TMA)");
 }
 // 3xTF32: split A and X into (hi, lo) TF32 parts in stream-ordered scratch, then the tcgen05/TMEM kernel.
 template <typename Cfg, bool ACC>
 static int launch_tf32x3(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
-                         int tiles_m, int tiles_n, int group_m, cudaStream_t s)
+                         int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
 {
     const int64_t ldA2 = (K + 3) / 4 * 4, ldX2 = (K + 3) / 4 * 4;  // A is stored transposed: K contiguous, M columns
     float* parts = nullptr;  // [A^T_hi | A^T_lo | X_hi | X_lo]
@@ -255,7 +267,8 @@ static int launch_tf32x3(void* D, const void* A, const void* X, int M, int N, in
     if (!rc) {
         int grid = tiles_m * tiles_n;
         if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
-        gemm_tf32x3_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mAh, mAl, mXh, mXl, (float*)D, M, N, K, ldd, tiles_m, tiles_n, group_m);
+        gemm_tf32x3_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mAh, mAl, mXh, mXl, (float*)D, M, N, K, ldd, tiles_m, tiles_n, group_m,
+                                                                           (const float*)Cin, ldc);
     }
     cudaFreeAsync(parts, s);
     return rc;
@@ -277,18 +290,21 @@ static cudaError_t attr_dmma_tma()
 
 #define SIMT_ENTRY(NAME, T, DT, CFG, EFF)                                                                          \
     {                                                                                                              \
-        NAME, DT, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF, false, false, 1, \
+        NAME, DT, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF, false, false,    \
+            CFG::MIN_BLOCKS,                                                                                       \
             {{launch_simt<T, CFG, false, false>, launch_simt<T, CFG, false, true>},                                \
              {launch_simt<T, CFG, true, false>, launch_simt<T, CFG, true, true>}},                                 \
-            attr_simt<T, CFG>                                                                                      \
+            attr_simt<T, CFG>,                                                                                     \
+            []() -> int { return occupancy_of(gemm_simt_kernel<T, CFG, true, false>, CFG::THREADS, CFG::SMEM); }   \
     }
 #define SIMT_F32X2_ENTRY(NAME, CFG, EFF)                                                                           \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F32, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
-            false, false, 1,                                                                                       \
+            false, false, CFG::MIN_BLOCKS,                                                                         \
             {{launch_simt_f32x2<CFG, false, false>, launch_simt_f32x2<CFG, false, true>},                          \
              {launch_simt_f32x2<CFG, true, false>, launch_simt_f32x2<CFG, true, true>}},                           \
-            attr_simt_f32x2<CFG>                                                                                   \
+            attr_simt_f32x2<CFG>,                                                                                  \
+            []() -> int { return occupancy_of(gemm_simt_f32x2_kernel<CFG, true, false>, CFG::THREADS, CFG::SMEM); } \
     }
 #define DMMA_ENTRY(NAME, CFG, EFF)                                                                                 \
     {                                                                                                              \
@@ -296,21 +312,22 @@ static cudaError_t attr_dmma_tma()
             false, false, 1,                                                                                       \
             {{launch_dmma<CFG, false, false>, launch_dmma<CFG, false, true>},                                      \
              {launch_dmma<CFG, true, false>, launch_dmma<CFG, true, true>}},                                       \
-            attr_dmma<CFG>                                                                                         \
+            attr_dmma<CFG>,                                                                                        \
+            []() -> int { return occupancy_of(gemm_dmma_kernel<CFG, true, false>, CFG::THREADS, CFG::SMEM); }      \
     }
 #define TF32X3_ENTRY(NAME, CFG, EFF)                                                                               \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F32, FAM_TF32X3, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF, \
             false, true, 1,                                                                                        \
             {{launch_tf32x3<CFG, false>, launch_tf32x3<CFG, true>}, {launch_tf32x3<CFG, false>, launch_tf32x3<CFG, true>}}, \
-            attr_tf32x3<CFG>                                                                                       \
+            attr_tf32x3<CFG>, nullptr                                                                              \
     }
 #define DMMA_TMA_ENTRY(NAME, CFG, EFF)                                                                             \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F64, FAM_DMMA, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
             true, true, CFG::MIN_BLOCKS,                                                                           \
             {{launch_needs_alignment, launch_needs_alignment}, {launch_dmma_tma<CFG, false>, launch_dmma_tma<CFG, true>}}, \
-            attr_dmma_tma<CFG>                                                                                     \
+            attr_dmma_tma<CFG>, nullptr                                                                            \
     }
 
 //                         T      WM WN BK ST MINB
@@ -335,6 +352,10 @@ using T64_64x64_x2 = DmmaTmaCfg<2, 2, 4, 4, 2, 3, 2>;  // 2 CTAs/SM (3 x 32 KiB 
 using T64_128x64_w8 = DmmaTmaCfg<2, 4, 8, 2, 2, 4>;  // 8 warps of 64x16
 using T64_32x32_x2 = DmmaTmaCfg<2, 2, 2, 2, 4, 3, 2>;  // 4 warps of 16x16, 2 CTAs/SM: 256^3..512^3 fill the 148 SMs
 using T64_64x32_x2 = DmmaTmaCfg<2, 2, 4, 2, 2, 4, 2>;  // 4 warps of 32x16, 2 CTAs/SM
+//                            WM WN RI NJ BK ST MINB
+using F2_64x64_w4 = F32x2Cfg<2, 2, 1, 8, 16, 4, 4>;  // 4 warps of 32x32 (thread 4x8)
+using F2_64x32_w4 = F32x2Cfg<2, 2, 1, 4, 16, 4, 4>;  // 4 warps of 32x16 (thread 4x4)
+using F2_32x32_w2 = F32x2Cfg<1, 2, 1, 4, 16, 4, 8>;  // 2 warps of 32x16
 using X3_128x256 = Tf32x3Cfg<256, 2>;  // 2 stages of 96 KiB, two 256-column TMEM accumulators
 using X3_128x128 = Tf32x3Cfg<128, 3>;  // 3 stages of 64 KiB
 
@@ -351,22 +372,26 @@ static const KernelInfo g_kernels[] = {
     /* 8 */ SIMT_ENTRY("simt_f32_64x64x16", float, JBLAS_B200_DT_F32, S32_64x64, 1.05f),
     /* 9 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x16_s6", T64_k16s6, 1.17f),   // 35.15-35.9 vs 30.2 TFLOP/s (8192^3, profiles/r1_sweep_*.json)
     /* 10 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x128x32_s3", T64_k32s3, 1.20f),  // 36.1-36.3 TFLOP/s: the AUTO choice for big shapes
-    /* 11 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x16", S32_128x128, 1.19f),
-    /* 12 */ SIMT_F32X2_ENTRY("simt_f32x2_128x64x16", S32_128x64, 1.22f),
-    /* 13 */ SIMT_F32X2_ENTRY("simt_f32x2_64x64x16", S32_64x64, 1.18f),
+    /* 11 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x16", S32_128x128, 1.22f),
+    /* 12 */ SIMT_F32X2_ENTRY("simt_f32x2_128x64x16", S32_128x64, 1.27f),
+    /* 13 */ SIMT_F32X2_ENTRY("simt_f32x2_64x64x16", S32_64x64, 1.215f),
     /* 14 */ SIMT_F32X2_ENTRY("simt_f32x2_128x128x32", S32_128x128_k32, 1.28f),
     /* 15 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4", T64_128x64, 1.02f),
     /* 16 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4", T64_96x64, 1.01f),
     /* 17 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x64_s3", T64_64x64_k64, 1.01f),
     /* 18 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4_w8", T64_96x64_w8, 1.17f),
-    /* 19 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.175f),
+    /* 19 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.14f),
     /* 20 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4_w8", T64_128x64_w8, 1.185f),
     /* 21 */ TF32X3_ENTRY("tf32x3_tcgen05_f32_128x256x32_s2", X3_128x256, 1.00f),
     /* 22 */ TF32X3_ENTRY("tf32x3_tcgen05_f32_128x128x32_s3", X3_128x128, 0.80f),
     /* 23 */ DMMA_TMA_ENTRY("dmma_tma_f64_32x32x64_s3_x2", T64_32x32_x2, 1.06f),
     /* 24 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x32x32_s4_x2", T64_64x32_x2, 1.125f),
+    /* 25 */ SIMT_F32X2_ENTRY("simt_f32x2_64x64x16_w4", F2_64x64_w4, 1.125f),
+    /* 26 */ SIMT_F32X2_ENTRY("simt_f32x2_64x32x16_w4", F2_64x32_w4, 1.00f),
+    /* 27 */ SIMT_F32X2_ENTRY("simt_f32x2_32x32x16_w2", F2_32x32_w2, 1.00f),
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
+static int g_occ[NUM_KERNELS] = {0};  // measured residency (filled at init); 0 = unknown, the planner uses ctas_per_sm
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
 
 // ---------------------------------------------------------------------------------------------------------
@@ -377,6 +402,16 @@ struct Plan {
     int tiles_m, tiles_n, group_m;
     bool aligned;
 };
+
+// Fraction of an SM's issue rate that `warps` resident warps of these kernels sustain (measured on lone CTAs of 2, 4 and
+// 8 warps, profiles/r1_size_sweep_f32_per_kernel.json; the persistent 4-warp DMMA CTAs show the same 0.8).
+static double sm_rate(int warps)
+{
+    if (warps >= 8) return 1.0;
+    if (warps >= 4) return 0.78 + (warps - 4) * 0.055;
+    if (warps >= 2) return 0.49 + (warps - 2) * 0.145;
+    return 0.25 * (warps > 0 ? warps : 1);
+}
 
 static bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -421,9 +456,20 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
         // pipeline fill and epilogue): measured, profiles/r1_size_sweep_per_kernel.json
         double waves = (double)((rounds - 1) * k.ctas_per_sm) + (last_share < k.ctas_per_sm ? 1.25 * last_share : (double)last_share);
         int warps = k.threads / 32;
-        double t = waves * per_tile;
-        double single = per_tile * 4.0 / (warps < 4 ? warps : 4);  // a lone CTA with <4 warps cannot fill an SM
-        if (single > t) t = single;
+        double t;
+        if (k.persistent) {
+            t = waves * per_tile;
+            double single = per_tile * 4.0 / (warps < 4 ? warps : 4);  // a lone CTA with <4 warps cannot fill an SM
+            if (single > t) t = single;
+        } else {
+            // one CTA per tile: the busiest SM runs n tiles, c at a time; a batch of j co-resident CTAs advances at the
+            // rate j*warps resident warps sustain (sm_rate: latency-bound below ~8 warps)
+            const int c = g_occ[i] > 0 ? g_occ[i] : k.ctas_per_sm;
+            const int64_t n = (tiles + num_sms - 1) / num_sms;
+            const int64_t full = n / c, rem = n % c;
+            t = (double)full * per_tile * c / sm_rate(c * warps);
+            if (rem) t += per_tile * (double)rem / sm_rate((int)rem * warps);
+        }
         t /= k.eff;
         if (best < 0 || t < best_t) { best = i; best_t = t; }
     }
@@ -471,26 +517,51 @@ __global__ void realign_kernel(T* __restrict__ dst, int64_t ldd, const T* __rest
     if (r >= rows) return;
     for (int c = blockIdx.y; c < cols; c += gridDim.y) dst[(size_t)c * ldd + r] = src[(size_t)c * lds + r];
 }
+// Prologue of D = A*(X + C) (src/memory_management.jl:72-76): dst = a + b, each element rounded once, written with an aligned
+// leading dimension.  A separate HBM-speed pass on purpose: it moves 3*K*N elements against 2*M*N*K flops (0.8 % of the
+// 8192^3 product), where adding inside the kernels would put a DADD per X fragment on the FP64 pipe of every tile row.
+template <typename T>
+__global__ void add_realign_kernel(T* __restrict__ dst, int64_t ldd, const T* __restrict__ a, int64_t lda_, const T* __restrict__ b,
+                                   int64_t ldb_, int rows, int cols)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int c = blockIdx.y; c < cols; c += gridDim.y) dst[(size_t)c * ldd + r] = a[(size_t)c * lda_ + r] + b[(size_t)c * ldb_ + r];
+}
 
 static int set_all_attrs()
 {
     if (g_ctx.attrs_set) return 0;
-    for (int i = 0; i < NUM_KERNELS; ++i) CUDA_TRY(g_kernels[i].set_attr());
+    for (int i = 0; i < NUM_KERNELS; ++i) {
+        CUDA_TRY(g_kernels[i].set_attr());
+        g_occ[i] = g_kernels[i].query_occ ? g_kernels[i].query_occ() : 0;
+    }
     g_ctx.attrs_set = true;
     return 0;
 }
 
+// The general device-side product:  D = A*(X [+ Xadd]) [+ Cin].
+//   Cin  == nullptr : overwrite (jmul!/initkernel!);  Cin == D : D += A*X (kernel!, src/kernels.jl:226);  any other Cin: the
+//                     planned fused form D = A*X + C -- every element's chain starts from C[i,j] instead of -0.0;
+//   Xadd != nullptr : the planned D = A*(X + C) -- X + Xadd is formed (one rounding per element) by add_realign_kernel.
 template <typename T>
-static int gemm_dev(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
-                    int64_t ldx, int accumulate, int selector, cudaStream_t s)
+static int gemm_dev_ex(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
+                       int64_t ldx, const T* Cin, int64_t ldc, const T* Xadd, int64_t ldxa, int selector, cudaStream_t s)
 {
     if (int rc = require_init()) return rc;
     if (int rc = validate(D, A, X, M, K, N, ldd, lda, ldx)) return rc;
     if (M == 0 || N == 0) return 0;
+    if (Cin && ldc < M) return fail(JBLAS_B200_EINVAL, "ldc=%lld < M=%lld", (long long)ldc, (long long)M);
+    if (Xadd && K > 0 && ldxa < K) return fail(JBLAS_B200_EINVAL, "ld of the matrix added to X = %lld < K=%lld", (long long)ldxa, (long long)K);
+    const int accumulate = Cin != nullptr;
     // s == NULL is the CUDA default stream, exactly as for any CUDA API: the caller's stream ordering is kept
-    if (K == 0) {  // empty contraction: jmul! would read X[1,j] out of bounds; defined here as D = 0 (or D unchanged)
+    if (K == 0) {  // empty contraction: jmul! would read X[1,j] out of bounds; defined here as D = 0 (or D = C / D unchanged)
         if (!accumulate) {
             zero_fill_kernel<T><<<g_ctx.num_sms * 4, 256, 0, s>>>(D, M, N, ldd);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+        } else if (Cin != D) {
+            realign_kernel<T><<<dim3((unsigned)((M + 255) / 256), (unsigned)(N < 65535 ? N : 65535)), 256, 0, s>>>(D, ldd, Cin, ldc, (int)M, (int)N);
             g_launches++;
             CUDA_TRY(cudaGetLastError());
         }
@@ -502,6 +573,15 @@ static int gemm_dev(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t 
     const int vec = 16 / (int)sizeof(T);
     T* tmpA = nullptr;
     T* tmpX = nullptr;
+    if (Xadd) {
+        const int64_t ld2 = (K + vec - 1) / vec * vec;
+        CUDA_TRY(cudaMallocAsync((void**)&tmpX, (size_t)ld2 * N * sizeof(T), s));
+        add_realign_kernel<T><<<dim3((unsigned)((K + 255) / 256), (unsigned)(N < 65535 ? N : 65535)), 256, 0, s>>>(tmpX, ld2, X, ldx, Xadd, ldxa,
+                                                                                                                 (int)K, (int)N);
+        g_launches++;
+        X = tmpX;
+        ldx = ld2;
+    }
     if (2.0 * (double)M * (double)N * (double)K >= 1.0e9) {
         if (!is_aligned16(A) || lda % vec) {
             const int64_t ld2 = (M + vec - 1) / vec * vec;
@@ -526,7 +606,7 @@ static int gemm_dev(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t 
     if (!rc) {
         const KernelInfo& k = g_kernels[p.kidx];
         rc = k.launch[p.aligned ? 1 : 0][accumulate ? 1 : 0](D, A, X, (int)M, (int)N, (int)K, ldd, lda, ldx, p.tiles_m, p.tiles_n,
-                                                             p.group_m, s);
+                                                             p.group_m, s, Cin, ldc);
     }
     if (tmpA) cudaFreeAsync(tmpA, s);
     if (tmpX) cudaFreeAsync(tmpX, s);
@@ -534,6 +614,12 @@ static int gemm_dev(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t 
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+template <typename T>
+static int gemm_dev(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
+                    int64_t ldx, int accumulate, int selector, cudaStream_t s)
+{
+    return gemm_dev_ex<T>(dtype, D, A, X, M, K, N, ldd, lda, ldx, accumulate ? D : nullptr, ldd, nullptr, 0, selector, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -685,6 +771,63 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
     return 0;
 }
 
+// Host-pointer form of the fused products: plain staging (everything up, one product, D down) on the compute stream.
+// These are convenience entries for host callers; the pipelined path above is the one the benchmark times.
+template <typename T>
+static int fused_host(int dtype, T* D, const T* A, const T* X, const T* C, int64_t M, int64_t K, int64_t N, int64_t ldd,
+                      int64_t lda, int64_t ldx, int64_t ldc, bool x_plus_c, int selector)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = require_init()) return rc;
+    if (int rc = validate(D, A, X, M, K, N, ldd, lda, ldx)) return rc;
+    if (M == 0 || N == 0) return 0;
+    const int64_t crows = x_plus_c ? K : M;
+    if (crows > 0 && (!C || ldc < crows)) return fail(JBLAS_B200_EINVAL, "C is NULL or ldc=%lld < %lld rows", (long long)ldc, (long long)crows);
+    const size_t es = sizeof(T);
+    const int vec = 16 / (int)es;
+    const int64_t dM = (M + vec - 1) / vec * vec, dK = (K + vec - 1) / vec * vec, dC = x_plus_c ? dK : dM;
+    cudaStream_t s = g_ctx.stream;
+    T *dD = nullptr, *dA = nullptr, *dX = nullptr, *dCm = nullptr;
+    auto release = [&]() {
+        if (dD) cudaFreeAsync(dD, s);
+        if (dA) cudaFreeAsync(dA, s);
+        if (dX) cudaFreeAsync(dX, s);
+        if (dCm) cudaFreeAsync(dCm, s);
+    };
+    cudaError_t e = cudaMallocAsync((void**)&dD, (size_t)dM * N * es, s);
+    if (e == cudaSuccess && K > 0) e = cudaMallocAsync((void**)&dA, (size_t)dM * K * es, s);
+    if (e == cudaSuccess && K > 0) e = cudaMallocAsync((void**)&dX, (size_t)dK * N * es, s);
+    if (e == cudaSuccess && crows > 0) e = cudaMallocAsync((void**)&dCm, (size_t)dC * N * es, s);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        release();
+        return fail(JBLAS_B200_ENOMEM, "device staging for the fused product: %s", cudaGetErrorString(e));
+    }
+    int rc = 0;
+    auto up = [&](T* dst, int64_t dld, const T* src, int64_t sld, int64_t rows, int64_t cols) {
+        if (rc || rows == 0 || cols == 0) return;
+        cudaError_t ce = cudaMemcpy2DAsync(dst, dld * es, src, sld * es, rows * es, cols, cudaMemcpyHostToDevice, s);
+        if (ce != cudaSuccess) rc = fail(JBLAS_B200_ECUDA, "H2D: %s", cudaGetErrorString(ce));
+    };
+    cudaEventRecord(g_ctx.ev0, s);
+    up(dA, dM, A, lda, M, K);
+    up(dX, dK, X, ldx, K, N);
+    up(dCm, dC, C, ldc, crows, N);
+    if (!rc)
+        rc = x_plus_c ? gemm_dev_ex<T>(dtype, dD, dA, dX, M, K, N, dM, dM, dK, nullptr, 0, K > 0 ? dCm : nullptr, dC, selector, s)
+                      : gemm_dev_ex<T>(dtype, dD, dA, dX, M, K, N, dM, dM, dK, dCm, dC, nullptr, 0, selector, s);
+    if (!rc) {
+        cudaError_t ce = cudaMemcpy2DAsync(D, ldd * es, dD, dM * es, M * es, N, cudaMemcpyDeviceToHost, s);
+        if (ce != cudaSuccess) rc = fail(JBLAS_B200_ECUDA, "D2H: %s", cudaGetErrorString(ce));
+    }
+    cudaEventRecord(g_ctx.ev1, s);
+    release();
+    cudaError_t ce = cudaStreamSynchronize(s);
+    if (!rc && ce != cudaSuccess) rc = fail(JBLAS_B200_ECUDA, "fused product: %s", cudaGetErrorString(ce));
+    if (!rc) cudaEventElapsedTime(&g_ctx.last_ms, g_ctx.ev0, g_ctx.ev1);
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // exported C ABI
 // ---------------------------------------------------------------------------------------------------------
@@ -767,6 +910,34 @@ int jblas_b200_shutdown(void)
     g_ctx = Context();
     return 0;
 }
+
+// ---- fused forms (src/memory_management.jl:72-76) ----
+#define FUSED_DEV(SUFFIX, T, DT)                                                                                                   \
+    int jblas_b200_gemm_plus_c_##SUFFIX##_dev(T* D, const T* A, const T* X, const T* C, int64_t M, int64_t K, int64_t N,           \
+                                              int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int kernel, void* stream)        \
+    {                                                                                                                              \
+        if (!C && M > 0 && N > 0) return fail(JBLAS_B200_EINVAL, "C is NULL");                                                     \
+        return gemm_dev_ex<T>(DT, D, A, X, M, K, N, ldd, lda, ldx, C, ldc, nullptr, 0, kernel, (cudaStream_t)stream);              \
+    }                                                                                                                              \
+    int jblas_b200_gemm_x_plus_c_##SUFFIX##_dev(T* D, const T* A, const T* X, const T* C, int64_t M, int64_t K, int64_t N,         \
+                                                int64_t ldd, int64_t lda, int64_t ldx, int64_t ldc, int kernel, void* stream)      \
+    {                                                                                                                              \
+        if (!C && K > 0 && N > 0 && M > 0) return fail(JBLAS_B200_EINVAL, "C is NULL");                                            \
+        return gemm_dev_ex<T>(DT, D, A, X, M, K, N, ldd, lda, ldx, nullptr, 0, C, ldc, kernel, (cudaStream_t)stream);              \
+    }                                                                                                                              \
+    int jblas_b200_gemm_plus_c_##SUFFIX(T* D, const T* A, const T* X, const T* C, int64_t M, int64_t K, int64_t N, int64_t ldd,    \
+                                        int64_t lda, int64_t ldx, int64_t ldc, int kernel)                                         \
+    {                                                                                                                              \
+        return fused_host<T>(DT, D, A, X, C, M, K, N, ldd, lda, ldx, ldc, false, kernel);                                          \
+    }                                                                                                                              \
+    int jblas_b200_gemm_x_plus_c_##SUFFIX(T* D, const T* A, const T* X, const T* C, int64_t M, int64_t K, int64_t N, int64_t ldd,  \
+                                          int64_t lda, int64_t ldx, int64_t ldc, int kernel)                                       \
+    {                                                                                                                              \
+        return fused_host<T>(DT, D, A, X, C, M, K, N, ldd, lda, ldx, ldc, true, kernel);                                           \
+    }
+FUSED_DEV(f64, double, JBLAS_B200_DT_F64)
+FUSED_DEV(f32, float, JBLAS_B200_DT_F32)
+#undef FUSED_DEV
 
 int jblas_b200_gemm_f64_dev(double* D, const double* A, const double* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
                             int64_t lda, int64_t ldx, int accumulate, int kernel, void* stream)

@@ -40,8 +40,8 @@ struct DmmaCfg {
 
 template <typename Cfg, bool ALIGNED, bool ACC>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
-gemm_dmma_kernel(double* __restrict__ D, const double* __restrict__ A, const double* __restrict__ X, int M, int N, int K,
-                 int64_t ldd, int64_t lda, int64_t ldx, int tiles_m, int tiles_n, int group_m)
+gemm_dmma_kernel(double* D, const double* __restrict__ A, const double* __restrict__ X, int M, int N, int K,
+                 int64_t ldd, int64_t lda, int64_t ldx, int tiles_m, int tiles_n, int group_m, const double* Cin, int64_t ldc)
 {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
     constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB, THREADS = Cfg::THREADS;
@@ -64,7 +64,7 @@ gemm_dmma_kernel(double* __restrict__ D, const double* __restrict__ A, const dou
             for (int c = 0; c < 2; ++c) {
                 if constexpr (ACC) {
                     int gm = m0 + wm * 64 + mi * 8 + g, gn = n0 + wn * 32 + ni * 8 + 2 * t + c;
-                    acc[mi][ni][c] = (gm < M && gn < N) ? D[(size_t)gn * ldd + gm] : 0.0;
+                    acc[mi][ni][c] = (gm < M && gn < N) ? Cin[(size_t)gn * ldc + gm] : 0.0;
                 } else {
                     acc[mi][ni][c] = -0.0;
                 }

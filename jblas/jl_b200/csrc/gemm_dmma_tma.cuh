@@ -160,8 +160,8 @@ __device__ __forceinline__ void dmma_consume_stage(double (&acc)[Cfg::MI][Cfg::N
 template <typename Cfg, bool ACC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS)
 gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
-                     double* __restrict__ D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m,
-                     uint64_t l2_policy_a, uint64_t l2_policy_x, int* __restrict__ tile_ctr)
+                     double* D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m,
+                     uint64_t l2_policy_a, uint64_t l2_policy_x, int* __restrict__ tile_ctr, const double* Cin, int64_t ldc)
 {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, KSUB = Cfg::KSUB, STAGES = Cfg::STAGES;
     constexpr int MI = Cfg::MI, NI = Cfg::NI;
@@ -283,7 +283,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     if constexpr (ACC) {
                         int gm = m0 + wrow0 + (mi >> 1) * 16 + pi_g + 4 * (mi & 1);
                         int gn = n0 + wcol0 + ni * 8 + (c ? sg_c1 : sg_c0);
-                        acc[mi][ni][c] = (gm < M && gn < N) ? D[(size_t)gn * ldd + gm] : 0.0;
+                        acc[mi][ni][c] = (gm < M && gn < N) ? Cin[(size_t)gn * ldc + gm] : 0.0;
                     } else {
                         acc[mi][ni][c] = -0.0;
                     }

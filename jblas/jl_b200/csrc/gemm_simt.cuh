@@ -8,7 +8,8 @@
 // multiply-adds -- exactly the reference's  d = A[i,1]*X[1,j]; d = fma(A[i,n], X[n,j], d)  (src/gemm.jl:86,165).
 //   * accumulators start at -0.0: fma(a, b, -0.0) == a*b for every a, b (including signed zeros, Inf, NaN), so
 //     the first step reproduces the reference's plain rounded product (initialize_block) without a special case;
-//   * ACC (kernel! semantics, src/kernels.jl:226) starts from the existing D instead;
+//   * ACC (kernel! semantics, src/kernels.jl:226) starts from an existing matrix instead: Cin == D is the reference's
+//     D += A*X, any other Cin is the planned fused form D = A*X + C (src/memory_management.jl:72-76);
 //   * no split-K, no tree reduction; the K tail runs a bounded loop instead of multiplying zero padding (so a
 //     -0.0 result is not turned into +0.0 by fma(0, 0, -0.0)).
 // The result therefore matches oracle/oracle_gemm.c bit for bit on finite inputs.
@@ -24,6 +25,7 @@ struct SimtCfg {
     static constexpr int THREADS = WM * WN * 32;
     static constexpr int VEC = 16 / (int)sizeof(T);  // elements per 16-byte shared-memory load
     static constexpr int NI = 8 / VEC;               // 16-byte A loads per thread per k
+    static constexpr int WARPS_M = WM, RI = NI, NJ = 8;  // (gemm_simt_f32x2.cuh reads its thread tile from these)
     static constexpr int LDA = BM;                   // sA[k][m]: reads are contiguous in m -> conflict-free
     static constexpr int LDB = BK + VEC;             // sB[n][k]: +16 B pitch puts the 4 n-lanes in distinct banks
     static constexpr int STAGE_ELEMS = BK * LDA + BN * LDB;
@@ -38,8 +40,8 @@ struct alignas(16) Vec16 {
 
 template <typename T, typename Cfg, bool ALIGNED, bool ACC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS)
-gemm_simt_kernel(T* __restrict__ D, const T* __restrict__ A, const T* __restrict__ X, int M, int N, int K, int64_t ldd,
-                 int64_t lda, int64_t ldx, int tiles_m, int tiles_n, int group_m)
+gemm_simt_kernel(T* D, const T* __restrict__ A, const T* __restrict__ X, int M, int N, int K, int64_t ldd,
+                 int64_t lda, int64_t ldx, int tiles_m, int tiles_n, int group_m, const T* Cin, int64_t ldc)
 {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, VEC = Cfg::VEC, NI = Cfg::NI;
     constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB, THREADS = Cfg::THREADS;
@@ -70,7 +72,7 @@ gemm_simt_kernel(T* __restrict__ D, const T* __restrict__ A, const T* __restrict
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     int gm = m0 + row_base + i * 8 * VEC + v;
-                    acc[j][i * VEC + v] = (gm < M && gn < N) ? D[(size_t)gn * ldd + gm] : T(0);
+                    acc[j][i * VEC + v] = (gm < M && gn < N) ? Cin[(size_t)gn * ldc + gm] : T(0);
                 }
         }
     } else {

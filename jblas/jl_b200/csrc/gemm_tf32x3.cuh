@@ -164,7 +164,7 @@ template <typename Cfg, bool ACC>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                    const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo,
-                   float* __restrict__ D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m)
+                   float* D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m, const float* Cin, int64_t ldc)
 {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
     extern __shared__ unsigned char smem_raw[];
@@ -281,7 +281,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                         if (gn < N) {
                             float* p = D + (size_t)gn * ldd + gm;
                             float v = __uint_as_float(r[j]);
-                            if constexpr (ACC) v += *p;
+                            if constexpr (ACC) v += Cin[(size_t)gn * ldc + gm];
                             *p = v;
                         }
                     }
