@@ -12,12 +12,14 @@
 #   kernel!(pD, pA, pX, K)      src/kernels.jl:239-241   D += A*X on raw pointers
 #   initkernel!(pD, pA, pX, K)  src/kernels.jl:273-275   D  = A*X on raw pointers
 #   Kernel{Mk,Pk,stride_AD,stride_X,N}   src/kernel_structure.jl:8-9
+#   gemm_plus_c!(D, A, X, C)    D = A*X + C    } the fused forms the reference planned but never wrote
+#   gemm_x_plus_c!(D, A, X, C)  D = A*(X + C)  } (src/memory_management.jl:72-76)
 # Accepted matrix types: anything with `pointer`, `size`, `stride(·,2)` and unit row stride -- MMatrix{M,N,T}
 # (the reference's type; `pointer(A)` is a stable dense column-major buffer, src/gemm.jl:309-311) and
 # Matrix{T}/StridedMatrix{T}, T in {Float64, Float32}.
 module jBLASB200
 
-export jmul!, gemm!, fastmul!, kernel!, initkernel!, Kernel, init, shutdown
+export jmul!, gemm!, fastmul!, kernel!, initkernel!, Kernel, init, shutdown, gemm_plus_c!, gemm_x_plus_c!
 
 const libjblas_b200 = get(ENV, "JBLAS_B200_LIB", joinpath(@__DIR__, "..", "jblas", "jl_b200", "libjblas_b200.so"))
 
@@ -89,6 +91,23 @@ for (T, gemm, kern, initk) in ((Float64, :jblas_b200_gemm_f64, :jblas_b200_kerne
     end
 end
 
+for (T, plusc, xplusc) in ((Float64, :jblas_b200_gemm_plus_c_f64, :jblas_b200_gemm_x_plus_c_f64),
+                           (Float32, :jblas_b200_gemm_plus_c_f32, :jblas_b200_gemm_x_plus_c_f32))
+    for (fn, sym, crows) in ((:_gemm_plus_c!, plusc, :M), (:_gemm_x_plus_c!, xplusc, :N))
+        @eval function $fn(D::AbstractMatrix{$T}, A::AbstractMatrix{$T}, X::AbstractMatrix{$T}, C::AbstractMatrix{$T}, selector::Cint)
+            M, N, P = _dims(D, A, X)
+            (size(C) == ($crows, P) && stride(C, 1) == 1) || throw(DimensionMismatch("C must be $($crows)x$(P), column-major"))
+            ensure_init()
+            GC.@preserve D A X C begin
+                check(ccall(($(QuoteNode(sym)), libjblas_b200), Cint,
+                            (Ptr{$T}, Ptr{$T}, Ptr{$T}, Ptr{$T}, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Cint),
+                            pointer(D), pointer(A), pointer(X), pointer(C), M, N, P, _ld(D), _ld(A), _ld(X), _ld(C), selector))
+            end
+            D
+        end
+    end
+end
+
 _default_selector(::Type{Float64}) = F64_AUTO
 _default_selector(::Type{Float32}) = F32_EXACT
 _exact_selector(::Type{Float64}) = F64_SIMT
@@ -110,5 +129,12 @@ const gemm! = jmul!
 "fastmul!(D, A, X) (src/kernels.jl:202-208): exact-chain kernels, any row count."
 fastmul!(D::AbstractMatrix{T}, A::AbstractMatrix{T}, X::AbstractMatrix{T}) where {T<:Union{Float64,Float32}} =
     _gemm!(D, A, X, false, _exact_selector(T))
+
+"gemm_plus_c!(D, A, X, C): D = A*X + C; every element's fma chain starts from C[i,j] (kernel!'s accumulate with the start read from C)."
+gemm_plus_c!(D::AbstractMatrix{T}, A::AbstractMatrix{T}, X::AbstractMatrix{T}, C::AbstractMatrix{T};
+             kernel::Cint = _default_selector(T)) where {T<:Union{Float64,Float32}} = _gemm_plus_c!(D, A, X, C, kernel)
+"gemm_x_plus_c!(D, A, X, C): D = A*(X + C), C sized like X; X + C is rounded once per element."
+gemm_x_plus_c!(D::AbstractMatrix{T}, A::AbstractMatrix{T}, X::AbstractMatrix{T}, C::AbstractMatrix{T};
+               kernel::Cint = _default_selector(T)) where {T<:Union{Float64,Float32}} = _gemm_x_plus_c!(D, A, X, C, kernel)
 
 end # module
