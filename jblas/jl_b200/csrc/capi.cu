@@ -517,6 +517,53 @@ __global__ void realign_kernel(T* __restrict__ dst, int64_t ldd, const T* __rest
     if (r >= rows) return;
     for (int c = blockIdx.y; c < cols; c += gridDim.y) dst[(size_t)c * ldd + r] = src[(size_t)c * lds + r];
 }
+// One launch re-aligns up to two operands.  128 threads per 16-byte-row-group x 8-column patch: a thread reads R = 16/sizeof(T)
+// consecutive rows of 8 columns with scalar loads (the source is only element-aligned; 8*R independent loads in flight) and
+// writes one 16-byte vector per column (the destination has an aligned base and leading dimension; its padding rows get 0).
+struct RealignJob {
+    const void* src;
+    void* dst;
+    int64_t lds, ldd;
+    int rows, cols, row_patches, patches;
+};
+template <typename T>
+static RealignJob make_realign_job(const T* src, int64_t lds, T* dst, int64_t ldd, int64_t rows, int64_t cols)
+{
+    constexpr int R = 16 / (int)sizeof(T);
+    RealignJob j;
+    j.src = src; j.dst = dst; j.lds = lds; j.ldd = ldd; j.rows = (int)rows; j.cols = (int)cols;
+    j.row_patches = (int)((rows + 128 * R - 1) / (128 * R));
+    j.patches = j.row_patches * (int)((cols + 7) / 8);
+    return j;
+}
+template <typename T>
+__global__ void __launch_bounds__(128) realign2_kernel(const RealignJob j0, const RealignJob j1)
+{
+    constexpr int R = 16 / (int)sizeof(T);
+    int b = blockIdx.x;
+    const bool second = b >= j0.patches;
+    const RealignJob& j = second ? j1 : j0;
+    if (second) b -= j0.patches;
+    const int rp = b % j.row_patches, cp = b / j.row_patches;
+    const int r = (rp * 128 + threadIdx.x) * R;
+    if (r >= j.rows) return;
+    const T* __restrict__ src = static_cast<const T*>(j.src);
+    T* __restrict__ dst = static_cast<T*>(j.dst);
+    struct alignas(16) V { T v[R]; };
+    V v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int cc = cp * 8 + c;
+#pragma unroll
+        for (int i = 0; i < R; ++i) v[c].v[i] = (cc < j.cols && r + i < j.rows) ? src[(size_t)cc * j.lds + r + i] : T(0);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int cc = cp * 8 + c;
+        if (cc < j.cols) *reinterpret_cast<V*>(dst + (size_t)cc * j.ldd + r) = v[c];
+    }
+}
+
 // Prologue of D = A*(X + C) (src/memory_management.jl:72-76): dst = a + b, each element rounded once, written with an aligned
 // leading dimension.  A separate HBM-speed pass on purpose: it moves 3*K*N elements against 2*M*N*K flops (0.8 % of the
 // 8192^3 product), where adding inside the kernels would put a DADD per X fragment on the FP64 pipe of every tile row.
@@ -583,21 +630,26 @@ static int gemm_dev_ex(int dtype, T* D, const T* A, const T* X, int64_t M, int64
         ldx = ld2;
     }
     if (2.0 * (double)M * (double)N * (double)K >= 1.0e9) {
+        RealignJob jobs[2];
+        int njobs = 0;
         if (!is_aligned16(A) || lda % vec) {
             const int64_t ld2 = (M + vec - 1) / vec * vec;
             CUDA_TRY(cudaMallocAsync((void**)&tmpA, (size_t)ld2 * K * sizeof(T), s));
-            realign_kernel<T><<<dim3((unsigned)((M + 255) / 256), (unsigned)(K < 65535 ? K : 65535)), 256, 0, s>>>(tmpA, ld2, A, lda, (int)M, (int)K);
-            g_launches++;
+            jobs[njobs++] = make_realign_job<T>(A, lda, tmpA, ld2, M, K);
             A = tmpA;
             lda = ld2;
         }
         if (!is_aligned16(X) || ldx % vec) {
             const int64_t ld2 = (K + vec - 1) / vec * vec;
             CUDA_TRY(cudaMallocAsync((void**)&tmpX, (size_t)ld2 * N * sizeof(T), s));
-            realign_kernel<T><<<dim3((unsigned)((K + 255) / 256), (unsigned)(N < 65535 ? N : 65535)), 256, 0, s>>>(tmpX, ld2, X, ldx, (int)K, (int)N);
-            g_launches++;
+            jobs[njobs++] = make_realign_job<T>(X, ldx, tmpX, ld2, K, N);
             X = tmpX;
             ldx = ld2;
+        }
+        if (njobs) {  // both operands in ONE launch
+            if (njobs == 1) { jobs[1] = jobs[0]; jobs[1].patches = 0; }
+            realign2_kernel<T><<<(unsigned)(jobs[0].patches + jobs[1].patches), 128, 0, s>>>(jobs[0], jobs[1]);
+            g_launches++;
         }
     }
     Plan p;

@@ -370,6 +370,21 @@ def test_config_ragged_1023x777x4097(jb):
     assert bits_equal(D, want)
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_ragged_operands_are_realigned_in_one_pass(jb, dt):
+    """>= 1 GFLOP with odd leading dimensions / odd row counts: A and X are re-aligned into scratch by one launch
+    (realign2_kernel: row groups of 16 bytes, partial last group, 8-column patches with a partial last patch)."""
+    M, K, N = 1021, 1027, 515  # 1.08 GFLOP; 1021 and 1027 are odd and not multiples of 4
+    A, X = randn_f((M, K), dt, ld=M + 2), randn_f((K, N), dt, SEED_X, ld=K + 6)
+    want = oracle.oracle_gemm(np.asfortranarray(A), np.asfortranarray(X))
+    got = _run_dev(jb, A, X, jb.F64_SIMT if dt == np.float64 else jb.F32_EXACT)
+    assert bits_equal(got, want)
+    if dt == np.float64:
+        assert "re-aligning" in jb.plan(M, K, N, lda=M + 2, ldx=K + 6)["staging"]
+        ok, worst = oracle.error_bound_ok(_run_dev(jb, A, X, jb.F64_AUTO), want, np.asfortranarray(A), np.asfortranarray(X))
+        assert ok, worst
+
+
 def test_config_tall_skinny_65536x64x64(jb):
     M, N, K = 65536, 64, 64
     A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)

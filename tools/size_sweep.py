@@ -17,6 +17,8 @@ ALL = "--all" in sys.argv
 dtypes = [a for a in sys.argv[1:] if a.startswith("float")] or ["float64", "float32"]
 names = jb.kernel_names()
 shapes = [(n, n, n) for n in (128, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144)] + [(8192, 512, 8192), (512, 8192, 512), (4096, 4096, 256), (256, 4096, 4096), (10000, 3000, 7000)]
+if "--c4" in sys.argv:  # BASELINE configs[3]: the ragged and the tall-skinny shape
+    shapes = [(1023, 777, 4097), (65536, 64, 64), (1024, 776, 4096)]
 for dtype in dtypes:
     for M, N, K in shapes:
         A = jb.mrandn(M, K, dtype, seed=1); X = jb.mrandn(K, N, dtype, seed=2); D = jb.empty_colmajor(M, N, dtype)
