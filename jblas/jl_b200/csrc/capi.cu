@@ -204,6 +204,22 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType 
     return 0;
 }
 
+// 3-D: dim2 = product index of a batch (element stride `stride2`)
+static int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t batch, uint64_t ld, uint64_t stride2,
+                        uint32_t box_r, uint32_t box_c)
+{
+    if (int rc = get_encode_tiled()) return rc;
+    cuuint64_t gdim[3] = {rows, cols, batch};
+    cuuint64_t gstride[2] = {ld * 8, stride2 * 8};
+    cuuint32_t box[3] = {box_r, box_c, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(JBLAS_B200_ECUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 template <typename Cfg, bool ACC>
 static int launch_dmma_tma(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
                            int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
@@ -1060,6 +1076,32 @@ int jblas_b200_initkernel_f32(float* pD, const float* pA, const float* pX, int64
 
 }  // extern "C" (templates cannot have C linkage)
 
+// Batched products too big for one warp (M or P > 32), Float64, 16-byte aligned: the persistent TMA/DMMA GEMM kernel with 3-D
+// tensor maps -- every tile of every product is one entry of the same dynamically scheduled tile list, so the TMA producer
+// streams from product to product without draining the pipeline.  BLAS names here: D(MxN) = A(MxK) * X(KxN) per product.
+template <typename Cfg>
+static int launch_dmma_tma_batched(double* D, const double* A, const double* X, int M, int K, int N, int64_t batch, int64_t strideD,
+                                   int64_t strideA, int64_t strideX, cudaStream_t s)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_done = true;
+    }
+    CUtensorMap mapA, mapX;
+    if (int rc = make_tmap_3d(&mapA, A, (uint64_t)M, (uint64_t)K, (uint64_t)batch, (uint64_t)M, (uint64_t)strideA, 16, 16)) return rc;
+    if (int rc = make_tmap_3d(&mapX, X, (uint64_t)K, (uint64_t)N, (uint64_t)batch, (uint64_t)K, (uint64_t)strideX, 16, Cfg::BN)) return rc;
+    const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM, tiles_n = (N + Cfg::BN - 1) / Cfg::BN;
+    const int64_t tiles = (int64_t)tiles_m * tiles_n * batch;
+    if (tiles > 0x7fffffffLL) return fail(JBLAS_B200_EINVAL, "batch too large: %lld tiles", (long long)tiles);
+    int64_t grid = (int64_t)g_ctx.num_sms * Cfg::MIN_BLOCKS;
+    if (grid > tiles) grid = tiles;
+    int* ctr = g_ctx.tile_ctr + 2 * (g_tile_ctr_seq.fetch_add(1, std::memory_order_relaxed) % kTileCtrSlots);
+    gemm_dmma_tma_kernel<Cfg, false, true><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, s>>>(
+        mapA, mapX, D, M, N, K, (int64_t)M, tiles_m, tiles_n, tiles_m, kL2EvictNormal, kL2EvictNormal, ctr, nullptr, 0, (int)batch, strideD);
+    return 0;
+}
+
 // fastmul!-class batched small products, device pointers, jBLAS dimension names (D MxP, A MxN, X NxP).
 template <typename T>
 static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t N, int64_t P, int64_t batch, int64_t strideD,
@@ -1072,6 +1114,63 @@ static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t 
     if (!D || !A || !X) return fail(JBLAS_B200_EINVAL, "NULL matrix pointer");
     if (strideD < M * P || strideA < M * N || strideX < N * P) return fail(JBLAS_B200_EINVAL, "batch stride smaller than one matrix");
     if (M > 4096 || N > 4096 || P > 4096) return fail(JBLAS_B200_EUNSUPPORTED, "fastmul_batched is for small matrices; use gemm");
+    if constexpr (sizeof(T) == 8) {
+        // Float64 up to 32 x N x 32: one warp per product on the tensor pipe, fragments loaded straight from HBM
+        static int force_simt = -1;
+        if (force_simt < 0) {
+            const char* e = getenv("JBLAS_B200_BATCHED_SIMT");  // A/B switch for measurements
+            force_simt = (e && atoi(e)) ? 1 : 0;
+        }
+        const bool tma_ok = (M > 32 || P > 32) && M % 2 == 0 && N % 2 == 0 && strideA % 2 == 0 && strideX % 2 == 0 && is_aligned16(A) &&
+                            is_aligned16(X) && batch <= 0x7fffffffLL;
+        if (!force_simt && tma_ok) {
+            int rc;
+            if (M <= 64 && P <= 64)
+                rc = launch_dmma_tma_batched<T64_64x64_x2>((double*)D, (const double*)A, (const double*)X, (int)M, (int)N, (int)P, batch, strideD, strideA, strideX, s);
+            else if (P <= 64)
+                rc = launch_dmma_tma_batched<T64_128x64_w8>((double*)D, (const double*)A, (const double*)X, (int)M, (int)N, (int)P, batch, strideD, strideA, strideX, s);
+            else
+                rc = launch_dmma_tma_batched<T64_k32s3>((double*)D, (const double*)A, (const double*)X, (int)M, (int)N, (int)P, batch, strideD, strideA, strideX, s);
+            if (rc) return rc;
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+            return 0;
+        }
+        if (!force_simt && M <= 128 && P <= 128) {  // beyond that a product is a GEMM of its own: the shared-memory limit below applies
+            const bool one_block = M <= 32 && P <= 32;
+            const int mblocks = (int)((M + 31) / 32), pblocks = (int)((P + 31) / 32);
+            const int mi = one_block ? (int)((M + 7) / 8) : 4, ni = one_block ? (int)((P + 7) / 8) : 4;
+            const bool tiny = mi == 1 && ni == 1 && N <= 16;
+            const int64_t warps_needed = tiny ? (batch + 3) / 4 : batch * mblocks * pblocks;
+            int64_t grid = (int64_t)g_ctx.num_sms * 16;  // 128-thread CTAs; the hardware keeps as many resident as registers allow
+            if (grid * 4 > warps_needed) grid = (warps_needed + 3) / 4;
+#define BATCHED_DMMA(MI_, NI_, KC_, U_)                                                                                              \
+    fastmul_batched_dmma_kernel<MI_, NI_, KC_, U_><<<(unsigned)grid, 128, 0, s>>>(                                                     \
+        (double*)D, (const double*)A, (const double*)X, (int)M, (int)N, (int)P, batch, strideD, strideA, strideX, mblocks, pblocks)
+#define BATCHED_DMMA_ROW(MI_)                                                                                                        \
+    switch (ni) {                                                                                                                    \
+        case 1: BATCHED_DMMA(MI_, 1, ((MI_) + 1 <= 4 ? 8 : 4), 1); break;                                                            \
+        case 2: BATCHED_DMMA(MI_, 2, ((MI_) + 2 <= 4 ? 8 : 4), 1); break;                                                            \
+        case 3: BATCHED_DMMA(MI_, 3, 4, 1); break;                                                                                   \
+        default: BATCHED_DMMA(MI_, 4, 4, 1); break;                                                                                  \
+    }
+            if (tiny) {
+                BATCHED_DMMA(1, 1, 2, 4);
+            } else {
+                switch (mi) {
+                    case 1: BATCHED_DMMA_ROW(1) break;
+                    case 2: BATCHED_DMMA_ROW(2) break;
+                    case 3: BATCHED_DMMA_ROW(3) break;
+                    default: BATCHED_DMMA_ROW(4) break;
+                }
+            }
+#undef BATCHED_DMMA_ROW
+#undef BATCHED_DMMA
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+            return 0;
+        }
+    }
     const int xpitch = (int)(N | 1);  // odd column pitch: the column lanes of a warp hit distinct banks
     const size_t slot = ((((size_t)M * N + (size_t)xpitch * P) + 1) & ~(size_t)1) * sizeof(T);  // even element count, as in the kernel
     if (2 * slot > (size_t)200 * 1024)

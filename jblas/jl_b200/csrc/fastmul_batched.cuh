@@ -13,6 +13,7 @@
 //   * every element is the reference chain: -0.0 start, fma over ascending k -- bit-identical to the oracle.
 #pragma once
 #include "common.cuh"
+#include "gemm_dmma.cuh"
 
 namespace jb {
 
@@ -115,6 +116,104 @@ fastmul_batched_kernel(T* __restrict__ D, const T* __restrict__ A, const T* __re
         __syncthreads();  // the stage is free for the load issued in the next iteration
     }
     cp_async_wait<0>();
+}
+
+// ---- Float64, products up to 32 x N x 32: tensor pipe, fragments straight from HBM ---------------------------------------
+// The SIMT kernel above spends ~450 shared-memory wavefronts per 16x32x14 product (3 loads per 4 FMAs) against ~60 to stage it:
+// shared-memory bandwidth, not HBM, bounds it (53 % of the HBM peak).  mma.sync.m8n8k4.f64 needs one 8-byte element per lane
+// per 8x4 / 4x8 fragment, and in column-major storage those fragments are sector-aligned already:
+//   A fragment (mi, k4): lane (g, t) reads A[mi*8 + g, k4*4 + t]  -> 4 runs of 64 contiguous bytes (g), one per column t
+//   X fragment (k4, ni): lane (g, t) reads X[k4*4 + t, ni*8 + g]  -> 8 runs of 32 contiguous bytes (t), one per column g
+// so ONE WARP owns one product (or one 32 x 32 block of it) and loads every fragment of a 32-deep k chunk with independent 8-byte global loads (for
+// 16x32x14 that is all 32 loads of the product in flight at once, 8 KB per warp), runs the DMMAs, and stores the accumulator
+// fragments (64-byte runs).  No shared memory, no barriers; latency is covered by the other resident warps.
+// DMMA is bit-identical to the sequential chain on B200 (tests/test_gemm_gpu.py), so results equal the SIMT kernel's.
+// Larger products (M or P > 32) are cut into 32 x 32 blocks of D, one warp each; the warps of one product run side by side,
+// so the A row-block / X column-block a sibling already fetched comes from L1/L2.  Tiny products (M, P <= 8, N <= 16) move
+// too few bytes per warp to cover the HBM latency, so a warp takes U = 4 consecutive products per iteration.
+template <int MI, int NI, int KC, int U>
+__global__ void __launch_bounds__(128, (MI * NI >= 12 ? 3 : 1))  // 3 CTAs/SM = 170 registers: the 4x4 grid otherwise takes 186 and drops to 2
+fastmul_batched_dmma_kernel(double* __restrict__ D, const double* __restrict__ A, const double* __restrict__ X, int M, int N, int P,
+                            int64_t batch, int64_t strideD, int64_t strideA, int64_t strideX, int mblocks, int pblocks)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nblk = mblocks * pblocks;
+    const int64_t items = (batch * nblk + U - 1) / U;  // a work item = U consecutive (product, block) pairs
+    for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < items; item += nwarps) {
+        const double* __restrict__ a[U];
+        const double* __restrict__ x[U];
+        int64_t prod[U];
+        int r0[U], c0[U];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t w = item * U + u;
+            live[u] = w < batch * nblk;
+            prod[u] = live[u] ? w / nblk : 0;
+            const int blk = live[u] ? (int)(w - prod[u] * nblk) : 0;
+            r0[u] = (blk % mblocks) * 32;
+            c0[u] = (blk / mblocks) * 32;
+            a[u] = A + prod[u] * strideA;
+            x[u] = X + prod[u] * strideX;
+        }
+        double acc[U][MI][NI][2];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni) acc[u][mi][ni][0] = acc[u][mi][ni][1] = -0.0;  // fma(a, b, -0.0) == a*b
+        for (int k0 = 0; k0 < N; k0 += 4 * KC) {
+            double af[U][KC][MI], bf[U][KC][NI];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk) {
+                    const int k = k0 + 4 * kk + t;
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi) {
+                        const int r = r0[u] + mi * 8 + g;
+                        af[u][kk][mi] = (live[u] && k < N && r < M) ? __ldg(a[u] + (size_t)k * M + r) : 0.0;
+                    }
+#pragma unroll
+                    for (int ni = 0; ni < NI; ++ni) {
+                        const int c = c0[u] + ni * 8 + g;
+                        // k >= N: (+0) * (-0.0) = -0.0 and c + (-0.0) == c for every c, so a padded step changes nothing
+                        bf[u][kk][ni] = (k < N) ? ((live[u] && c < P) ? __ldg(x[u] + (size_t)c * N + k) : 0.0) : -0.0;
+                    }
+                }
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+                if (k0 + 4 * kk < N) {  // warp-uniform
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                            for (int ni = 0; ni < NI; ++ni)
+                                dmma884(acc[u][mi][ni][0], acc[u][mi][ni][1], af[u][kk][mi], bf[u][kk][ni]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!live[u]) continue;
+            double* __restrict__ d = D + prod[u] * strideD;
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col = c0[u] + ni * 8 + 2 * t + c;
+                    if (col >= P) continue;
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi) {
+                        const int r = r0[u] + mi * 8 + g;
+                        if (r < M) d[(size_t)col * M + r] = acc[u][mi][ni][c];
+                    }
+                }
+        }
+    }
 }
 
 }  // namespace jb

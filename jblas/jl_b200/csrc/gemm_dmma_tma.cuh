@@ -89,6 +89,15 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+// 3-D form (third coordinate = the product of a batch; fastmul_batched on the same pipeline)
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ double lds_f64(uint32_t addr)
 {
     double v;
@@ -157,11 +166,14 @@ __device__ __forceinline__ void dmma_consume_stage(double (&acc)[Cfg::MI][Cfg::N
     }
 }
 
-template <typename Cfg, bool ACC>
+// BATCHED: the tile list runs over `batch` independent products (3-D tensor maps, third coordinate = product; D of product b
+// starts batch_stride_d elements after that of product b-1) -- the fastmul!-class batch for products too big for one warp.
+template <typename Cfg, bool ACC, bool BATCHED = false>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS)
 gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
                      double* D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m,
-                     uint64_t l2_policy_a, uint64_t l2_policy_x, int* __restrict__ tile_ctr, const double* Cin, int64_t ldc)
+                     uint64_t l2_policy_a, uint64_t l2_policy_x, int* __restrict__ tile_ctr, const double* Cin, int64_t ldc,
+                     int batch = 1, int64_t batch_stride_d = 0)
 {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, KSUB = Cfg::KSUB, STAGES = Cfg::STAGES;
     constexpr int MI = Cfg::MI, NI = Cfg::NI;
@@ -183,7 +195,8 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
     __syncthreads();
 
-    const int num_tiles = tiles_m * tiles_n;
+    const int tiles_per_product = tiles_m * tiles_n;
+    const int num_tiles = tiles_per_product * (BATCHED ? batch : 1);
     const int KT = (K + BK - 1) / BK;
 
     if (warp >= Cfg::CONSUMER_WARPS) {
@@ -200,7 +213,8 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 // (tile_ctr == nullptr: static stride, kept for A/B measurements -- JBLAS_B200_STATIC_TILES=1)
                 const int next = tile_ctr ? atomicAdd(tile_ctr, 1) + (int)gridDim.x : tile + (int)gridDim.x;
                 int tm, tn;
-                raster(tile, tiles_m, tiles_n, group_m, tm, tn);
+                const int prod = BATCHED ? tile / tiles_per_product : 0;
+                raster(BATCHED ? tile - prod * tiles_per_product : tile, tiles_m, tiles_n, group_m, tm, tn);
                 const int m0 = tm * BM, n0 = tn * BN;
                 for (int kt = 0; kt < KT; ++kt) {
                     mbar_wait(&empty[s], phase ^ 1);
@@ -213,9 +227,16 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         unsigned char* sa = st + sub * Cfg::SUB_BYTES;
 #pragma unroll
                         // L2 eviction priorities per operand are chosen by the host (capi.cu: launch_dmma_tma).
-                        for (int mo = 0; mo < BM / 16; ++mo)
-                            tma_load_2d_hint(sa + mo * 2048, &mapA, &full[s], m0 + mo * 16, k0, l2_policy_a);
-                        tma_load_2d_hint(sa + Cfg::A_SUB_BYTES, &mapX, &full[s], k0, n0, l2_policy_x);
+                        for (int mo = 0; mo < BM / 16; ++mo) {
+                            if constexpr (BATCHED)
+                                tma_load_3d_hint(sa + mo * 2048, &mapA, &full[s], m0 + mo * 16, k0, prod, l2_policy_a);
+                            else
+                                tma_load_2d_hint(sa + mo * 2048, &mapA, &full[s], m0 + mo * 16, k0, l2_policy_a);
+                        }
+                        if constexpr (BATCHED)
+                            tma_load_3d_hint(sa + Cfg::A_SUB_BYTES, &mapX, &full[s], k0, n0, prod, l2_policy_x);
+                        else
+                            tma_load_2d_hint(sa + Cfg::A_SUB_BYTES, &mapX, &full[s], k0, n0, l2_policy_x);
                     }
                     if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
@@ -270,8 +291,10 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int tile = stage_tile[s];
         if (tile < 0) break;
         int tm, tn;
-        raster(tile, tiles_m, tiles_n, group_m, tm, tn);
+        const int prod = BATCHED ? tile / tiles_per_product : 0;
+        raster(BATCHED ? tile - prod * tiles_per_product : tile, tiles_m, tiles_n, group_m, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
+        double* const Dp = D + (BATCHED ? (int64_t)prod * batch_stride_d : 0);
 
         double acc[MI][NI][2];
 #pragma unroll
@@ -308,7 +331,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             for (int c = 0; c < 2; ++c) {
                 const int gn = n0 + wcol0 + ni * 8 + (c ? sg_c1 : sg_c0);
                 if (gn >= N) continue;
-                double* dcol = D + (size_t)gn * ldd;
+                double* dcol = Dp + (size_t)gn * ldd;
 #pragma unroll
                 for (int mi = 0; mi < MI; ++mi) {
                     const int gm = m0 + wrow0 + (mi >> 1) * 16 + pi_g + 4 * (mi & 1);

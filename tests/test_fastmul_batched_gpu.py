@@ -9,7 +9,11 @@ from tests.helpers import bits_equal
 pytestmark = pytest.mark.gpu
 
 # jBLAS names (M, N, P): D is MxP, A is MxN, X is NxP.  First entries: the reference script's small shapes
-SHAPES = [(16, 32, 14), (32, 32, 6), (32, 32, 24), (1, 1, 1), (5, 3, 7), (13, 40, 5), (40, 8, 5), (64, 64, 64), (3, 100, 2), (97, 11, 33)]
+#   Float64 with M, P <= 32 runs the one-warp-per-product DMMA kernel (MI x NI fragment grids 1..4, k chunks of 32 or 16, k tails),
+#   everything else the shared-memory SIMT kernel
+SHAPES = [(16, 32, 14), (32, 32, 6), (32, 32, 24), (1, 1, 1), (5, 3, 7), (13, 40, 5), (40, 8, 5), (64, 64, 64), (3, 100, 2), (97, 11, 33),
+          (25, 7, 31), (32, 70, 32), (8, 4, 8), (24, 33, 9), (9, 17, 24), (8, 16, 8), (20, 10, 130), (128, 5, 100),
+          (96, 34, 70), (130, 6, 40), (66, 130, 34)]  # Float64, even M and N, M or P > 32: the TMA/DMMA GEMM kernel over 3-D tensor maps
 
 
 def _to_np(t):
@@ -69,7 +73,7 @@ def test_fastmul_batched_argument_errors(jb):
         jb.fastmul_batched_(D, A.transpose(1, 2), X)  # row-major matrices
     with pytest.raises(TypeError):
         jb.fastmul_batched_(D, A.float(), X)
-    big = jb.empty_colmajor_batch(1, 256, 256)
+    big = jb.empty_colmajor_batch(1, 257, 257)  # odd: no TMA path, and too big for the shared-memory kernel
     with pytest.raises(jb.JblasB200Error):
         jb.fastmul_batched_(big, big, big)  # too large for the small-matrix kernel: use gemm
 
