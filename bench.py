@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the jmul! path on B200 (contract: see the task brief, section 4).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c4a|c4b|c5] [--kernel auto|dmma|simt]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c4a|c4b|c5|fb] [--kernel auto|dmma|simt]
 
 One "step" = one product D = A*X over one batch of synthetic N(0,1) input (mrandn, src/randmat.jl:5-14).
   N = 1  : BASELINE.json configs[1]  -- Float64 M=N=K=8192 (the config the metric is quoted on).
   N > 1  : the column-sharded mode: every rank owns an 8192-column block of X and D, A (8192x8192)
            lives on rank 0 and is broadcast in K panels overlapped with the local GEMM -> weak scaling,
            N = 1 being exactly configs[1].  `--workload c5` runs BASELINE configs[4] instead (32768^3 strong).
+`--workload fb` (N = 1 only) is the SURVEY 8f-1 row: 10^6 independent 16x32x14 Float64 fastmul! products in one launch, the
+one shape the reference publishes a time for (test/runtests.jl:110-122); HBM-bound, so its roofline object is in GB/s.
 Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference's own loop nest
 (oracle/jmul_baseline.c; Julia is not available) on rank 0 only.
 """
@@ -183,6 +185,122 @@ def load_peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+FB_SHAPE = (16, 32, 14, 1_000_000)  # jBLAS names M, N, P (D MxP = A MxN * X NxP) and the batch
+FB_PUBLISHED_NS = 127.921            # minimum time of ONE such product on the author's CPU, 1 thread
+
+
+def run_batched(args):
+    """--workload fb: batched fastmul! on one GPU.  Same JSON contract; the dominant kernel is HBM-bound."""
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import numpy as np
+    import torch
+
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--workload fb is a single-GPU workload (independent products: N GPUs = N replicas)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    from jblas.jl_b200 import build
+
+    build.build()
+    import jblas.jl_b200 as jb
+
+    jb.init(0)
+    M, N, P, batch = FB_SHAPE
+    A = jb.mrandn_batch(batch, M, N, "float64", seed=SEED_A)
+    X = jb.mrandn_batch(batch, N, P, "float64", seed=SEED_X)
+    D = jb.empty_colmajor_batch(batch, M, P, "float64", fill=float("nan"))
+    flops = 2.0 * M * N * P * batch
+    algo_bytes = (M * N + N * P + M * P) * 8 * batch  # every matrix read or written exactly once
+    for _ in range(max(args.warmup, 3)):
+        jb.fastmul_batched_(D, A, X)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = jb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        jb.fastmul_batched_(D, A, X)
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = jb.launch_count() - launches0
+    clocks = sampler.summary(t0, t1)
+    sampler.stop()
+    assert not torch.isnan(D).any().item()
+    peaks, peak_src = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo_bytes / (ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"fastmul_batched_dmma@{M}x{N}x{P}x{batch}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                "kernel": "fastmul_batched_dmma_kernel<2,2,8,1>", "kernel_ms": ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "flops_per_launch": flops, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src}; a copy bandwidth, 1 read : 1 write -- this "
+                "kernel reads 2.4 bytes per byte written, so a fraction slightly above 1 is possible)"}
+    # e2e: pinned host batches -> device -> product -> host, every step
+    Ah = A.cpu().pin_memory()
+    Xh = X.cpu().pin_memory()
+    Dh = torch.empty_like(D.cpu()).pin_memory()
+    steps = max(1, min(args.steps, 5))
+
+    def e2e_step():
+        A.copy_(Ah, non_blocking=True)
+        X.copy_(Xh, non_blocking=True)
+        jb.fastmul_batched_(D, A, X)
+        Dh.copy_(D, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step()
+    t = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    sec = (time.perf_counter() - t) / steps
+    e2e = {"value": flops / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": (M * N + N * P) * 8 * batch, "d2h_bytes_per_step": M * P * 8 * batch,
+           "steps": steps, "ms_per_step": 1e3 * sec, "api": "fastmul_batched_ on device batches fed from / drained to pinned host memory (PCIe-bound)"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle
+
+        nb = 200_000  # bounded sample: 200k of the 10^6 products (1.9 GB of the workload), repeated until ~10 s have passed
+        rng = np.random.Generator(np.random.PCG64(SEED_A))
+        Ac = rng.standard_normal((nb, N, M)).transpose(0, 2, 1)
+        Xc = rng.standard_normal((nb, P, N)).transpose(0, 2, 1)
+        Dc = np.empty((nb, P, M)).transpose(0, 2, 1)
+        oracle.fastmul_baseline_batched(Dc[:1000], Ac[:1000], Xc[:1000])
+        reps, sec_cpu = 0, 0.0
+        while sec_cpu < 10.0 and reps < 200:
+            t = time.perf_counter()
+            oracle.fastmul_baseline_batched(Dc, Ac, Xc)
+            sec_cpu += time.perf_counter() - t
+            reps += 1
+        ns_each = sec_cpu / (reps * nb) * 1e9
+        cpu = {"value": 2.0 * M * N * P / (ns_each * 1e-9) / 1e12, "unit": "TFLOP/s", "cores": 1, "kind": "port",
+               "sample": f"restatement of fastmul! (oracle/jmul_baseline.c, register-resident 2x14 zmm accumulators) over {nb} of the {batch} "
+                         f"products x {reps} passes, streaming from DRAM: {ns_each:.0f} ns per product on 1 thread (the reference publishes "
+                         f"{FB_PUBLISHED_NS} ns for one cache-resident product on the author's CPU); host has {os.cpu_count()} cores"}
+    value = flops / (ms * 1e-3) / 1e12
+    published_tflops = 2.0 * M * N * P / (FB_PUBLISHED_NS * 1e-9) / 1e12
+    line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / published_tflops, "dtype": "f64",
+            "data": "synthetic N(0,1), device-generated Philox (mrandn analogue)",
+            "config": {"workload": f"fastmul! batched: {batch} independent Float64 products D({M}x{P}) = A({M}x{N}) * X({N}x{P}) per launch (SURVEY 8f-1)",
+                       "products_per_s": batch / (ms * 1e-3), "ns_per_product": ms * 1e6 / batch,
+                       "vs_baseline_note": f"BASELINE.md publishes {FB_PUBLISHED_NS} ns per product (1 CPU thread, author's machine) = {published_tflops:.4f} TFLOP/s",
+                       "l2": f"inputs larger than L2: {algo_bytes / 2**20:.0f} MiB per step vs 126 MB L2"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    return 0
 
 
 def run_gpu(args):
@@ -428,7 +546,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["fb"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "dmma", "simt", "tf32x3"])
     ap.add_argument("--panel-k", type=int, default=2048)
     ap.add_argument("--first-panel-k", type=int, default=256, help="shorter first K panel of the A broadcast (0 = same as the others)")
@@ -436,7 +554,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large workloads)")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "fb":
+            raise SystemExit("--impl reference times the jmul! loop nest on the GEMM workloads; the fb leg reports its CPU figure in cpu_baseline")
         return run_reference(args)
+    if args.workload == "fb":
+        return run_batched(args)
     return run_gpu(args)
 
 

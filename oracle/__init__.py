@@ -16,6 +16,7 @@ from .cpu import (  # noqa: F401
     error_bound_ok,
     jmul_baseline,
     jmul_baseline_tile,
+    fastmul_baseline_batched,
     pick_kernel_size,
     num_threads,
 )

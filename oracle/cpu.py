@@ -148,5 +148,26 @@ def jmul_baseline(D, A, X, col_tiles=None, nthreads: int = 1, fill_edges: bool =
     return int(cov[0]), int(cov[1])
 
 
+def fastmul_baseline_batched(D, A, X):
+    """fastmul! (src/kernels.jl:43-130, 202-208) restated and applied to a batch: D[b] = A[b] @ X[b], float64.
+
+    Arrays are (batch, rows, cols) views of column-major matrices, i.e. strides (stride_b, 1, rows) in elements, as the
+    GPU batched entry takes them.  One thread (the reference is single-threaded)."""
+    batch, M, N = A.shape
+    _, _, P = X.shape
+    assert D.shape == (batch, M, P) and X.shape[1] == N and A.dtype == np.float64 == X.dtype == D.dtype
+    it = A.itemsize
+    for a, r, nm in ((A, M, "A"), (X, N, "X"), (D, M, "D")):
+        if a.size and (a.strides[1] != it or (a.shape[2] > 1 and a.strides[2] != r * it)):
+            raise ValueError(f"{nm}: every matrix must be dense column-major")
+    fn = lib().fastmul_baseline_batched_f64
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64] * 7
+    rc = fn(D.ctypes.data, A.ctypes.data, X.ctypes.data, M, N, P, batch, D.strides[0] // it, A.strides[0] // it, X.strides[0] // it)
+    if rc:
+        raise RuntimeError(f"fastmul_baseline_batched failed: {rc}")
+    return D
+
+
 def num_threads() -> int:
     return lib().oracle_num_threads()

@@ -236,3 +236,92 @@ int jmul_baseline_max_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* fastmul! (src/kernels.jl:43-130, 202-208), restated for the batched-products baseline        */
+/* ------------------------------------------------------------------------------------------ */
+/* The generated fastmul! keeps ALL of D in registers: Q = M/W row vectors x P columns of accumulators; the first contraction
+ * step is a plain product (mulinit, src/kernels.jl:3-23), every later step loads the Q vectors of A[:, n], broadcasts X[n, p]
+ * for each column p and does vmuladd (:91-100); D is stored once at the end (:112-117).  Restated here for the shapes whose
+ * accumulators fit the register file (Q*P <= 28 zmm / 12 ymm), M a multiple of the vector length; other shapes run the plain
+ * chain loops (same arithmetic, no claim about speed).  One thread, like the reference. */
+#define DEFINE_FASTMUL(NAME, VEC, VL, QMAX, PMAX, TARGET, LOADU, STOREU, SET1, MUL, FMADD)                          \
+    __attribute__((target(TARGET))) static int NAME(double *D, const double *A, const double *X, int64_t M,        \
+                                                    int64_t N, int64_t P)                                          \
+    {                                                                                                             \
+        if (M % VL || M / VL > QMAX || P > PMAX || (M / VL) * P > QMAX * PMAX || N < 1) return 0;                 \
+        const int Q = (int)(M / VL);                                                                              \
+        VEC acc[QMAX][PMAX], a[QMAX];                                                                             \
+        for (int q = 0; q < Q; ++q) a[q] = LOADU(A + q * VL);                                                     \
+        for (int p = 0; p < P; ++p) {                                                                             \
+            VEC x = SET1(X[p * N]);                                                                               \
+            for (int q = 0; q < Q; ++q) acc[q][p] = MUL(a[q], x);                                                 \
+        }                                                                                                         \
+        for (int64_t n = 1; n < N; ++n) {                                                                         \
+            for (int q = 0; q < Q; ++q) a[q] = LOADU(A + n * M + q * VL);                                         \
+            for (int p = 0; p < P; ++p) {                                                                         \
+                VEC x = SET1(X[n + p * N]);                                                                       \
+                for (int q = 0; q < Q; ++q) acc[q][p] = FMADD(a[q], x, acc[q][p]);                                \
+            }                                                                                                     \
+        }                                                                                                         \
+        for (int p = 0; p < P; ++p)                                                                               \
+            for (int q = 0; q < Q; ++q) STOREU(D + p * M + q * VL, acc[q][p]);                                    \
+        return 1;                                                                                                 \
+    }
+
+DEFINE_FASTMUL(fastmul_f64_avx512, __m512d, 8, 2, 14, "avx512f", _mm512_loadu_pd, _mm512_storeu_pd, _mm512_set1_pd, _mm512_mul_pd,
+               _mm512_fmadd_pd)
+DEFINE_FASTMUL(fastmul_f64_avx2, __m256d, 4, 2, 6, "avx2,fma", _mm256_loadu_pd, _mm256_storeu_pd, _mm256_set1_pd, _mm256_mul_pd,
+               _mm256_fmadd_pd)
+
+/* Specialised copy for the reference's published shape (16x32x14: Q = 2, P = 14, 28 zmm accumulators) with compile-time
+ * trip counts, so the compiler keeps the accumulators in registers exactly as the generated Julia code does. */
+__attribute__((target("avx512f"))) static void fastmul_f64_16x32x14_avx512(double *D, const double *A, const double *X)
+{
+    __m512d acc[2][14], a0 = _mm512_loadu_pd(A), a1 = _mm512_loadu_pd(A + 8);
+#pragma GCC unroll 14
+    for (int p = 0; p < 14; ++p) {
+        __m512d x = _mm512_set1_pd(X[p * 32]);
+        acc[0][p] = _mm512_mul_pd(a0, x);
+        acc[1][p] = _mm512_mul_pd(a1, x);
+    }
+    for (int n = 1; n < 32; ++n) {
+        a0 = _mm512_loadu_pd(A + n * 16);
+        a1 = _mm512_loadu_pd(A + n * 16 + 8);
+#pragma GCC unroll 14
+        for (int p = 0; p < 14; ++p) {
+            __m512d x = _mm512_set1_pd(X[n + p * 32]);
+            acc[0][p] = _mm512_fmadd_pd(a0, x, acc[0][p]);
+            acc[1][p] = _mm512_fmadd_pd(a1, x, acc[1][p]);
+        }
+    }
+#pragma GCC unroll 14
+    for (int p = 0; p < 14; ++p) {
+        _mm512_storeu_pd(D + p * 16, acc[0][p]);
+        _mm512_storeu_pd(D + p * 16 + 8, acc[1][p]);
+    }
+}
+
+/* `batch` independent products D_b(MxP) = A_b(MxN) * X_b(NxP), dense column-major, matrix b at b*stride; jBLAS dimension names. */
+int fastmul_baseline_batched_f64(double *D, const double *A, const double *X, int64_t M, int64_t N, int64_t P, int64_t batch,
+                                 int64_t strideD, int64_t strideA, int64_t strideX)
+{
+    if (M < 0 || N < 1 || P < 0 || batch < 0) return -1;
+    const int isa = jmul_baseline_isa();
+    for (int64_t b = 0; b < batch; ++b) {
+        double *d = D + b * strideD;
+        const double *a = A + b * strideA, *x = X + b * strideX;
+        if (isa == 512 && M == 16 && N == 32 && P == 14) {
+            fastmul_f64_16x32x14_avx512(d, a, x);
+            continue;
+        }
+        if ((isa == 512 && fastmul_f64_avx512(d, a, x, M, N, P)) || (isa == 256 && fastmul_f64_avx2(d, a, x, M, N, P))) continue;
+        for (int64_t p = 0; p < P; ++p)
+            for (int64_t i = 0; i < M; ++i) {
+                double v = a[i] * x[p * N];
+                for (int64_t n = 1; n < N; ++n) v = fma(a[i + n * M], x[n + p * N], v);
+                d[i + p * M] = v;
+            }
+    }
+    return 0;
+}

@@ -115,3 +115,19 @@ def test_baseline_threads_and_edges():
         r, c = oracle.jmul_baseline(D3, A, X, col_tiles=(1, 3))
         _, _, cols = oracle.jmul_baseline_tile(np.dtype(dt).itemsize)
         assert c == 2 * cols and bits_equal(D3[:r, cols:3 * cols], Do[:r, cols:3 * cols]) and np.isnan(D3[:, :cols]).all()
+
+
+@pytest.mark.parametrize("shape", [(16, 32, 14), (8, 5, 3), (16, 1, 14), (24, 9, 4), (5, 3, 7), (16, 32, 15), (32, 4, 2)], ids=str)
+def test_fastmul_baseline_batched_equals_chain_oracle(shape):
+    """The fastmul! restatement (register-resident D, src/kernels.jl:43-130) computes the same chain as oracle_gemm,
+    for the specialised 16x32x14 kernel, the generic SIMD kernel and the scalar fallback."""
+    M, N, P = shape
+    batch = 5
+    rng = np.random.Generator(np.random.PCG64(41))
+    A = np.ascontiguousarray(rng.standard_normal((batch, N, M))).transpose(0, 2, 1)  # (batch, M, N), column-major matrices
+    X = np.ascontiguousarray(rng.standard_normal((batch, P, N))).transpose(0, 2, 1)
+    D = np.full((batch, P, M), np.nan).transpose(0, 2, 1)
+    oracle.fastmul_baseline_batched(D, A, X)
+    for b in range(batch):
+        want = oracle.oracle_gemm(np.asfortranarray(A[b]), np.asfortranarray(X[b]))
+        assert np.ascontiguousarray(D[b]).tobytes() == np.ascontiguousarray(want).tobytes()

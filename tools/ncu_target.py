@@ -11,6 +11,18 @@ sys.path.insert(0, ROOT)
 import jblas.jl_b200 as jb  # noqa: E402
 from jblas.jl_b200 import api  # noqa: E402
 
+if sys.argv[1] == "batched":  # python tools/ncu_target.py batched M N P batch [reps]   (jBLAS names: D MxP = A MxN * X NxP)
+    M, N, P, batch = (int(v) for v in sys.argv[2:6])
+    reps = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+    jb.init(0)
+    A = jb.mrandn_batch(batch, M, N, "float64", seed=1)
+    X = jb.mrandn_batch(batch, N, P, "float64", seed=2)
+    D = jb.empty_colmajor_batch(batch, M, P, "float64")
+    for _ in range(reps):
+        jb.fastmul_batched_(D, A, X)
+    torch.cuda.synchronize()
+    print("done batched")
+    sys.exit(0)
 dtype, M, N, K, sel = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
 reps = int(sys.argv[6]) if len(sys.argv) > 6 else 3
 sel = {"auto": None, "dmma": jb.F64_DMMA, "simt": jb.F64_SIMT}.get(sel, None) if not sel.isdigit() else int(sel)
