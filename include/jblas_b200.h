@@ -138,6 +138,13 @@ int jblas_b200_fastmul_batched_f64_dev(double* D, const double* A, const double*
                                        int64_t batch, int64_t strideD, int64_t strideA, int64_t strideX, void* stream);
 int jblas_b200_fastmul_batched_f32_dev(float* D, const float* A, const float* X, int64_t M, int64_t N, int64_t P,
                                        int64_t batch, int64_t strideD, int64_t strideA, int64_t strideX, void* stream);
+/* Same on HOST pointers (what a Julia ccall on an Array{T,3} or a vector of MMatrix storage hits): synchronous; the batch is
+ * streamed through the device in chunks with H2D, the kernel and D2H overlapped.  Gaps between matrices (stride > matrix size)
+ * are neither read nor written. */
+int jblas_b200_fastmul_batched_f64(double* D, const double* A, const double* X, int64_t M, int64_t N, int64_t P, int64_t batch,
+                                   int64_t strideD, int64_t strideA, int64_t strideX);
+int jblas_b200_fastmul_batched_f32(float* D, const float* A, const float* X, int64_t M, int64_t N, int64_t P, int64_t batch,
+                                   int64_t strideD, int64_t strideA, int64_t strideX);
 
 /* ---- device memory / transfers (the shim owns no caller memory; these are conveniences) ------------ */
 int jblas_b200_alloc(void** dptr, size_t bytes);

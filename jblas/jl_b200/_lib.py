@@ -46,6 +46,8 @@ PROTOTYPES = {
     "jblas_b200_gemm_plus_c_f32": (c_int, _FUSED),
     "jblas_b200_gemm_x_plus_c_f64": (c_int, _FUSED),
     "jblas_b200_gemm_x_plus_c_f32": (c_int, _FUSED),
+    "jblas_b200_fastmul_batched_f64": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64]),
+    "jblas_b200_fastmul_batched_f32": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64]),
     "jblas_b200_fastmul_batched_f64_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "jblas_b200_fastmul_batched_f32_dev": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "jblas_b200_alloc": (c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),

@@ -288,32 +288,52 @@ def empty_colmajor_batch(batch: int, M: int, N: int, dtype="float64", device=Non
 def fastmul_batched_(D, A, X):
     """Batched fastmul! (src/kernels.jl:202-208 is the single-product form): D[b] = A[b] * X[b] for every b in one launch.
 
-    D, A, X are torch CUDA tensors of shape (batch, M, P), (batch, M, N), (batch, N, P) whose matrices are dense
-    column-major (strides (s, 1, rows) with s >= rows*cols).  Exact chain per element (bit-identical to the oracle)."""
-    import torch
+    D, A, X have shape (batch, M, P), (batch, M, N), (batch, N, P) and every matrix is dense column-major (strides
+    (s, 1, rows) with s >= rows*cols).  torch CUDA tensors take the device entry on the current stream; numpy arrays take
+    the host-pointer entry (chunked H2D / kernel / D2H pipeline, synchronous).  Exact chain per element (bit-identical to
+    the oracle)."""
+    dev = _is_torch(D)
 
     def desc(t, name):
-        if not _is_torch(t) or not t.is_cuda or t.dim() != 3:
-            raise ValueError(f"{name} must be a 3-D torch CUDA tensor (batch, rows, cols)")
-        if t.dtype not in (torch.float64, torch.float32):
-            raise TypeError(f"{name}: dtype {t.dtype} not supported")
-        b, r, c = t.shape
-        sb, sr, sc = t.stride()
-        if (r > 1 and sr != 1) or (c > 1 and sc != r):
-            raise ValueError(f"{name}: every matrix must be dense column-major (strides (s, 1, rows)), got {t.stride()}")
-        return b, r, c, (sb if b > 1 else r * c)
+        if dev:
+            import torch
 
-    bD, M, P, sD = desc(D, "D")
-    bA, M2, N, sA = desc(A, "A")
-    bX, N2, P2, sX = desc(X, "X")
-    if not (D.dtype == A.dtype == X.dtype):
+            if not _is_torch(t) or not t.is_cuda or t.dim() != 3:
+                raise ValueError(f"{name} must be a 3-D torch CUDA tensor (batch, rows, cols), like D")
+            if t.dtype not in (torch.float64, torch.float32):
+                raise TypeError(f"{name}: dtype {t.dtype} not supported")
+            strides, tag = t.stride(), (DT_F64 if t.dtype == torch.float64 else DT_F32)
+        else:
+            if not isinstance(t, np.ndarray) or t.ndim != 3:
+                raise ValueError(f"{name} must be a 3-D numpy array (batch, rows, cols), like D")
+            if t.dtype not in (np.float64, np.float32):
+                raise TypeError(f"{name}: dtype {t.dtype} not supported")
+            strides, tag = tuple(st // t.itemsize for st in t.strides), (DT_F64 if t.dtype == np.float64 else DT_F32)
+        b, r, c = t.shape
+        sb, sr, sc = strides
+        if (r > 1 and sr != 1) or (c > 1 and sc != r):
+            raise ValueError(f"{name}: every matrix must be dense column-major (strides (s, 1, rows)), got {strides}")
+        return b, r, c, (sb if b > 1 else r * c), tag
+
+    bD, M, P, sD, tD = desc(D, "D")
+    bA, M2, N, sA, tA = desc(A, "A")
+    bX, N2, P2, sX, tX = desc(X, "X")
+    if not (tD == tA == tX):
         raise TypeError("D, A and X must share one element type")
     if not (bD == bA == bX) or M2 != M or N2 != N or P2 != P:
         raise ValueError(f"shape mismatch: D {tuple(D.shape)}, A {tuple(A.shape)}, X {tuple(X.shape)}")
     init()
     L = _lib.lib()
-    fn = L.jblas_b200_fastmul_batched_f64_dev if D.dtype == torch.float64 else L.jblas_b200_fastmul_batched_f32_dev
-    check(fn(D.data_ptr(), A.data_ptr(), X.data_ptr(), M, N, P, bD, sD, sA, sX, torch.cuda.current_stream(D.device).cuda_stream))
+    if dev:
+        import torch
+
+        fn = L.jblas_b200_fastmul_batched_f64_dev if tD == DT_F64 else L.jblas_b200_fastmul_batched_f32_dev
+        check(fn(D.data_ptr(), A.data_ptr(), X.data_ptr(), M, N, P, bD, sD, sA, sX, torch.cuda.current_stream(D.device).cuda_stream))
+    else:
+        if not D.flags.writeable:
+            raise ValueError("D must be writeable")
+        fn = L.jblas_b200_fastmul_batched_f64 if tD == DT_F64 else L.jblas_b200_fastmul_batched_f32
+        check(fn(D.ctypes.data, A.ctypes.data, X.ctypes.data, M, N, P, bD, sD, sA, sX))
     return D
 
 

@@ -1199,8 +1199,82 @@ static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t 
     return 0;
 }
 
+// Host-pointer form: the batch is cut into chunks of ~32 MiB that travel H2D, are multiplied and travel back D2H on three
+// streams, three device slots deep, so PCIe (full duplex) and the kernel overlap.  PCIe-bound by construction (1.5 flop/B).
+template <typename T>
+static int fastmul_batched_host(T* D, const T* A, const T* X, int64_t M, int64_t N, int64_t P, int64_t batch, int64_t strideD,
+                                int64_t strideA, int64_t strideX)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = require_init()) return rc;
+    if (M < 0 || N < 0 || P < 0 || batch < 0) return fail(JBLAS_B200_EINVAL, "negative dimension");
+    if (batch == 0 || M == 0 || P == 0) return 0;
+    if (N == 0) return fail(JBLAS_B200_EINVAL, "empty contraction (N = 0) is not defined for fastmul_batched");
+    if (!D || !A || !X) return fail(JBLAS_B200_EINVAL, "NULL matrix pointer");
+    if (strideD < M * P || strideA < M * N || strideX < N * P) return fail(JBLAS_B200_EINVAL, "batch stride smaller than one matrix");
+    const size_t es = sizeof(T);
+    const int64_t eA = M * N, eX = N * P, eD = M * P;  // dense on the device
+    const size_t per_product = (size_t)(eA + eX + eD) * es;
+    int64_t nb = (int64_t)(((size_t)32 << 20) / per_product);
+    if (nb < 1) nb = 1;
+    if (nb > batch) nb = batch;
+    constexpr int SLOTS = 3;
+    if (int rc = ensure_ws(0, (size_t)SLOTS * nb * eD * es)) return rc;
+    if (int rc = ensure_ws(1, (size_t)SLOTS * nb * eA * es)) return rc;
+    if (int rc = ensure_ws(2, (size_t)SLOTS * nb * eX * es)) return rc;
+    static cudaEvent_t ev_in[SLOTS] = {nullptr}, ev_k[SLOTS] = {nullptr}, ev_out[SLOTS] = {nullptr};
+    for (int i = 0; i < SLOTS; ++i) {
+        if (!ev_in[i]) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t cs = g_ctx.copy_stream, ks = g_ctx.stream, os = g_ctx.d2h_stream;
+    auto copy = [&](void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, int64_t rows, cudaMemcpyKind kind,
+                    cudaStream_t st) -> cudaError_t {
+        if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * (size_t)rows, kind, st);  // dense: one run
+        return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, (size_t)rows, kind, st);  // strided batch: gaps untouched
+    };
+    CUDA_TRY(cudaEventRecord(g_ctx.ev0, cs));
+    int64_t c = 0;
+    for (int64_t b0 = 0; b0 < batch; b0 += nb, ++c) {
+        const int slot = (int)(c % SLOTS);
+        const int64_t n = batch - b0 < nb ? batch - b0 : nb;
+        T* dD = (T*)g_ctx.ws[0] + (size_t)slot * nb * eD;
+        T* dA = (T*)g_ctx.ws[1] + (size_t)slot * nb * eA;
+        T* dX = (T*)g_ctx.ws[2] + (size_t)slot * nb * eX;
+        if (c >= SLOTS) CUDA_TRY(cudaStreamWaitEvent(cs, ev_out[slot], 0));  // the slot's previous result has left the device
+        CUDA_TRY(copy(dA, eA * es, A + b0 * strideA, strideA * es, eA * es, n, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(copy(dX, eX * es, X + b0 * strideX, strideX * es, eX * es, n, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaEventRecord(ev_in[slot], cs));
+        CUDA_TRY(cudaStreamWaitEvent(ks, ev_in[slot], 0));
+        if (int rc = fastmul_batched_dev<T>(dD, dA, dX, M, N, P, n, eD, eA, eX, ks)) return rc;
+        CUDA_TRY(cudaEventRecord(ev_k[slot], ks));
+        CUDA_TRY(cudaStreamWaitEvent(os, ev_k[slot], 0));
+        CUDA_TRY(copy(D + b0 * strideD, strideD * es, dD, eD * es, eD * es, n, cudaMemcpyDeviceToHost, os));
+        CUDA_TRY(cudaEventRecord(ev_out[slot], os));
+    }
+    CUDA_TRY(cudaEventRecord(g_ctx.ev1, os));
+    CUDA_TRY(cudaStreamSynchronize(os));
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    CUDA_TRY(cudaStreamSynchronize(ks));
+    cudaEventElapsedTime(&g_ctx.last_ms, g_ctx.ev0, g_ctx.ev1);
+    return 0;
+}
+
 extern "C" {
 
+int jblas_b200_fastmul_batched_f64(double* D, const double* A, const double* X, int64_t M, int64_t N, int64_t P, int64_t batch,
+                                   int64_t strideD, int64_t strideA, int64_t strideX)
+{
+    return fastmul_batched_host<double>(D, A, X, M, N, P, batch, strideD, strideA, strideX);
+}
+int jblas_b200_fastmul_batched_f32(float* D, const float* A, const float* X, int64_t M, int64_t N, int64_t P, int64_t batch,
+                                   int64_t strideD, int64_t strideA, int64_t strideX)
+{
+    return fastmul_batched_host<float>(D, A, X, M, N, P, batch, strideD, strideA, strideX);
+}
 int jblas_b200_fastmul_batched_f64_dev(double* D, const double* A, const double* X, int64_t M, int64_t N, int64_t P, int64_t batch,
                                        int64_t strideD, int64_t strideA, int64_t strideX, void* stream)
 {

@@ -19,7 +19,7 @@
 # Matrix{T}/StridedMatrix{T}, T in {Float64, Float32}.
 module jBLASB200
 
-export jmul!, gemm!, fastmul!, kernel!, initkernel!, Kernel, init, shutdown, gemm_plus_c!, gemm_x_plus_c!
+export jmul!, gemm!, fastmul!, kernel!, initkernel!, Kernel, init, shutdown, gemm_plus_c!, gemm_x_plus_c!, fastmul_batched!
 
 const libjblas_b200 = get(ENV, "JBLAS_B200_LIB", joinpath(@__DIR__, "..", "jblas", "jl_b200", "libjblas_b200.so"))
 
@@ -136,5 +136,27 @@ gemm_plus_c!(D::AbstractMatrix{T}, A::AbstractMatrix{T}, X::AbstractMatrix{T}, C
 "gemm_x_plus_c!(D, A, X, C): D = A*(X + C), C sized like X; X + C is rounded once per element."
 gemm_x_plus_c!(D::AbstractMatrix{T}, A::AbstractMatrix{T}, X::AbstractMatrix{T}, C::AbstractMatrix{T};
                kernel::Cint = _default_selector(T)) where {T<:Union{Float64,Float32}} = _gemm_x_plus_c!(D, A, X, C, kernel)
+
+"""
+    fastmul_batched!(D::Array{T,3}, A::Array{T,3}, X::Array{T,3}) -> D
+
+`D[:,:,b] = A[:,:,b] * X[:,:,b]` for every `b` in ONE launch: the B200 form of `fastmul!` (src/kernels.jl:202-208) for a
+collection of small matrices (a dense `Array{T,3}` is exactly `batch` column-major matrices back to back).
+"""
+for (T, sym) in ((Float64, :jblas_b200_fastmul_batched_f64), (Float32, :jblas_b200_fastmul_batched_f32))
+    @eval function fastmul_batched!(D::Array{$T,3}, A::Array{$T,3}, X::Array{$T,3})
+        M, P, B = size(D)
+        MA, N, BA = size(A)
+        NX, PX, BX = size(X)
+        (MA == M && NX == N && PX == P && BA == B && BX == B) || throw(DimensionMismatch("D $(size(D)), A $(size(A)), X $(size(X))"))
+        ensure_init()
+        GC.@preserve D A X begin
+            check(ccall(($(QuoteNode(sym)), libjblas_b200), Cint,
+                        (Ptr{$T}, Ptr{$T}, Ptr{$T}, Int64, Int64, Int64, Int64, Int64, Int64, Int64),
+                        pointer(D), pointer(A), pointer(X), M, N, P, B, M * P, M * N, N * P))
+        end
+        D
+    end
+end
 
 end # module

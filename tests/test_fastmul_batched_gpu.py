@@ -95,3 +95,27 @@ def test_fastmul_batched_large_batch_throughput_shape(jb):
     ref = torch.bmm(A, X)
     bound = 2 * N * 2.0 ** -52 * torch.bmm(A.abs(), X.abs())
     assert ((D - ref).abs() <= bound).all()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_fastmul_batched_host_pointer_pipeline(jb, dt):
+    """Host-pointer entry (what a Julia ccall on an Array{T,3} hits): chunked H2D / kernel / D2H over three device slots;
+    several chunks, a ragged last chunk, and gaps between matrices that must be neither read into D nor overwritten."""
+    M, N, P = 16, 32, 14
+    es = np.dtype(dt).itemsize
+    batch = int(3.4 * (32 << 20) / ((M * N + N * P + M * P) * es))  # 3.4 chunks of 32 MiB
+    rng = np.random.Generator(np.random.PCG64(77))
+    gap = 6
+    sA = np.ascontiguousarray(rng.standard_normal((batch, M * N + gap)).astype(dt))
+    sX = np.ascontiguousarray(rng.standard_normal((batch, N * P)).astype(dt))
+    sD = np.full((batch, M * P + gap), np.nan, dtype=dt)
+    A = sA[:, : M * N].reshape(batch, N, M).transpose(0, 2, 1)
+    X = sX.reshape(batch, P, N).transpose(0, 2, 1)
+    D = sD[:, : M * P].reshape(batch, P, M).transpose(0, 2, 1)
+    assert jb.fastmul_batched_(D, A, X) is D
+    assert np.isnan(sD[:, M * P:]).all() and not np.isnan(sD[:, : M * P]).any()
+    for b in sorted({0, 1, batch // 3, batch // 2, batch - 2, batch - 1}):
+        want = oracle.oracle_gemm(np.asfortranarray(A[b]), np.asfortranarray(X[b]))
+        assert bits_equal(np.asfortranarray(D[b]), want), b
+    with pytest.raises(ValueError):
+        jb.fastmul_batched_(D, A, X[:-1])
