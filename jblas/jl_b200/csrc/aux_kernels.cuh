@@ -192,4 +192,76 @@ __global__ void __launch_bounds__(256) probe_ffma2_tile_kernel(float* out, int i
     if (s == 0x123456789abcdefull) out[0] = 1.f;
 }
 
+// The exact-FP32 kernel's inner loop (gemm_simt_f32x2.cuh) on a resident shared-memory tile, without any global traffic:
+// what the FFMA2 stream sustains WITH its shared-memory operand loads.  MODE bits: 1 = __syncthreads per 32-deep k-tile,
+// 2 = A through four LDS.64 instead of two LDS.128, 4 = no X loads (registers reused), 8 = no A loads.
+template <int MODE, int NJ = 8, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) probe_ffma2_lds_kernel(float* out, int iters)
+{
+    constexpr int BM = 128, BN = 16 * NJ, BK = (NJ > 8 ? 16 : 32), LDA = BM, LDB = BK + 4;
+    __shared__ __align__(16) float sAb[BK * LDA];
+    __shared__ __align__(16) float sBb[BN * LDB];
+    for (int i = threadIdx.x; i < BK * LDA; i += 256) sAb[i] = 1e-3f * (float)((i * 7 + 3) % 13);
+    for (int i = threadIdx.x; i < BN * LDB; i += 256) sBb[i] = 1e-3f * (float)((i * 5 + 1) % 11);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp % 2, wn = warp / 2, tx = lane & 7, ty = lane >> 3;
+    const float* sA = sAb + wm * 64 + tx * 4;
+    const float* sB = sBb + (wn * 4 * NJ + ty) * LDB;
+    uint64_t acc[NJ][4];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[j][p] = 0ull;
+    float2 b[NJ];
+    ulonglong2 a[2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) b[j] = make_float2(1e-3f * j, 2e-3f * j);
+    a[0] = make_ulonglong2(0x3a83126f3a83126full, 0x3a83126f3a83126full);
+    a[1] = a[0];
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int kc = 0; kc < BK; kc += 2) {
+            if constexpr (!(MODE & 4)) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const float2*>(sB + j * 4 * LDB + kc);
+            }
+#pragma unroll
+            for (int kv = 0; kv < 2; ++kv) {
+                if constexpr (!(MODE & 8)) {
+                    if constexpr (MODE & 2) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            a[i].x = *reinterpret_cast<const uint64_t*>(sA + (kc + kv) * LDA + i * 32);
+                            a[i].y = *reinterpret_cast<const uint64_t*>(sA + (kc + kv) * LDA + i * 32 + 2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const ulonglong2*>(sA + (kc + kv) * LDA + i * 32);
+                    }
+                }
+                uint64_t bb[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const float bs = kv ? b[j].y : b[j].x;
+                    asm("mov.b64 %0, {%1, %1};\n" : "=l"(bb[j]) : "f"(bs));
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const uint64_t ap = (p & 1) ? a[p >> 1].y : a[p >> 1].x;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(acc[j][p]) : "l"(ap), "l"(bb[j]));
+                }
+            }
+        }
+        if constexpr (MODE & 1) __syncthreads();
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) s ^= acc[j][p];
+    if (s == 0x123456789abcdefull) out[0] = 1.f;
+}
+
 }  // namespace jb

@@ -174,10 +174,15 @@ gemm_simt_f32x2_kernel(float* D, const float* __restrict__ A, const float* __res
             float* dcol = D + (size_t)(n0 + col_base + j * 4) * ldd + m0 + row_base;
 #pragma unroll
             for (int i = 0; i < RI; ++i) {
+#ifdef F32X2_STORE64
+                *reinterpret_cast<uint64_t*>(dcol + i * 32) = acc[j][2 * i];
+                *reinterpret_cast<uint64_t*>(dcol + i * 32 + 2) = acc[j][2 * i + 1];
+#else
                 ulonglong2 o;
                 o.x = acc[j][2 * i];
                 o.y = acc[j][2 * i + 1];
                 *reinterpret_cast<ulonglong2*>(dcol + i * 32) = o;
+#endif
             }
         }
     } else {
