@@ -375,7 +375,7 @@ def probe_pipe(kind: str, iters: int = 20000):
     kinds = {"dfma": 0, "dmma": 1, "ffma": 2, "dmma_tile": 3, "dfma_tile": 4, "ffma_tile": 5, "ffma2_tile": 6}
     # 'ffma2_lds<mode>': the exact-FP32 kernel's inner loop with its shared-memory loads (mode bits: aux_kernels.cuh)
     if kind.startswith("ffma2_wide"):  # 8 x 16 thread tile: 0 = loads, 1 = loads + barrier, 2 = no loads, 3 = no loads + barrier
-        k = 23 + int(kind[len("ffma2_wide"):] or 0)
+        k = 100 + int(kind[len("ffma2_wide"):] or 0)
     else:
         k = 7 + int(kind[len("ffma2_lds"):] or 0) if kind.startswith("ffma2_lds") else kinds[kind]
     check(_lib.lib().jblas_b200_probe_pipe(k, iters, ctypes.byref(tf), ctypes.byref(ms)))

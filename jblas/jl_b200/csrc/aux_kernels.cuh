@@ -205,7 +205,12 @@ __global__ void __launch_bounds__(256, MINB) probe_ffma2_lds_kernel(float* out, 
     for (int i = threadIdx.x; i < BN * LDB; i += 256) sBb[i] = 1e-3f * (float)((i * 5 + 1) % 11);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wm = warp % 2, wn = warp / 2, tx = lane & 7, ty = lane >> 3;
+    // MODE bit 16: lanes of a quarter-warp = 2 row groups x 4 column groups (instead of 8 row groups of one column group)
+    // MODE bit 32: quarter q = 4 row groups x 2 column groups chosen so that the two quarters of each half-warp read DISJOINT
+    //              chunks of both operands (an LDS.128 is served per half-warp; duplicates across its two quarters cost a wavefront)
+    const int wm = warp % 2, wn = warp / 2, qq = lane >> 3, ll = lane & 7;
+    const int tx = (MODE & 32) ? ((ll & 3) + 4 * (qq & 1)) : ((MODE & 16) ? (lane >> 2) : (lane & 7));
+    const int ty = (MODE & 32) ? ((ll >> 2) + 2 * ((qq & 1) ^ (qq >> 1))) : ((MODE & 16) ? (lane & 3) : (lane >> 3));
     const float* sA = sAb + wm * 64 + tx * 4;
     const float* sB = sBb + (wn * 4 * NJ + ty) * LDB;
     uint64_t acc[NJ][4];

@@ -1416,18 +1416,21 @@ int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms_out)
         } else if (kind == 6) {  // FFMA2 (fma.rn.f32x2), 8x8 outer-product pattern, 2 CTAs per SM
             probe_ffma2_tile_kernel<<<g_ctx.num_sms * 2, threads, 0, s>>>((float*)out, iters, 1.0000001f, 1e-9f);
             flops = 2.0 * 64 * iters * (double)g_ctx.num_sms * 2 * threads;
-        } else if (kind >= 7 && kind < 23) {  // FFMA2 inner loop of the exact-FP32 kernel with its shared-memory operand loads (mode = kind - 7)
+        } else if (kind >= 7 && kind < 7 + 64) {  // FFMA2 inner loop of the exact-FP32 kernel with its shared-memory operand loads (mode = kind - 7)
             const int grid = g_ctx.num_sms * 2;
             switch (kind - 7) {
 #define LDS_PROBE(MODE_) case MODE_: probe_ffma2_lds_kernel<MODE_><<<grid, threads, 0, s>>>((float*)out, iters); break;
                 LDS_PROBE(0) LDS_PROBE(1) LDS_PROBE(2) LDS_PROBE(3) LDS_PROBE(4) LDS_PROBE(5) LDS_PROBE(6) LDS_PROBE(7)
                 LDS_PROBE(8) LDS_PROBE(9) LDS_PROBE(10) LDS_PROBE(11) LDS_PROBE(12) LDS_PROBE(13) LDS_PROBE(14) LDS_PROBE(15)
+                LDS_PROBE(16) LDS_PROBE(18) LDS_PROBE(20) LDS_PROBE(24) LDS_PROBE(22)
+                LDS_PROBE(32) LDS_PROBE(33) LDS_PROBE(36) LDS_PROBE(40)
+                default: cudaFree(out); return fail(JBLAS_B200_EINVAL, "probe mode %d is not built", kind - 7);
 #undef LDS_PROBE
             }
             flops = 2.0 * 64 * 32 * iters * (double)grid * threads;  // 32 k per iteration, 64 FMAs per thread per k
-        } else if (kind >= 23 && kind < 27) {  // the same loop with an 8 x 16 thread tile (one CTA per SM), 16 k per iteration
+        } else if (kind >= 100 && kind < 104) {  // the same loop with an 8 x 16 thread tile (one CTA per SM), 16 k per iteration
             const int grid = g_ctx.num_sms;
-            switch (kind - 23) {
+            switch (kind - 100) {
                 case 0: probe_ffma2_lds_kernel<0, 16, 1><<<grid, threads, 0, s>>>((float*)out, iters); break;
                 case 1: probe_ffma2_lds_kernel<1, 16, 1><<<grid, threads, 0, s>>>((float*)out, iters); break;
                 case 2: probe_ffma2_lds_kernel<12, 16, 1><<<grid, threads, 0, s>>>((float*)out, iters); break;
