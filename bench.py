@@ -375,6 +375,13 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # untimed pre-warm: ~1 s of steps so clocks and power reach their steady state before the W warm-up steps (a cold box
+    # measured 32.2 ms/step, the same command a minute later 31.0)
+    # (a fixed COUNT derived from the workload, identical on every rank: each step contains collectives)
+    n_pre = int(min(40, 1.0 / max(flops_step / world / 36e12, 1e-3)))
+    for _ in range(n_pre):
+        sg(D, A, X)
+    torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         sg(D, A, X)
     barrier()
