@@ -156,6 +156,19 @@ int jblas_b200_host_register(void* host, size_t bytes);
 int jblas_b200_host_unregister(void* host);
 int jblas_b200_stream_sync(void* stream);
 
+/* ---- peer memory for the multi-GPU mode (one process per GPU on one node) ----------------
+ * The exchange step of the column-sharded product is "A becomes visible on every GPU".  Instead of a collective whose
+ * kernels take SMs from the GEMM, the owner EXPORTS its A allocation, every other process MAPS it (CUDA IPC) and pulls
+ * K panels with the copy engines over NVLink (jblas_b200_copy_async on a side stream), overlapped with the multiplies.
+ *   ipc_export : handle (64 bytes) + byte offset of `dptr` inside its allocation, to be sent to the peers by any means
+ *   ipc_open   : maps the peer allocation into this process; *peer_ptr addresses the same bytes as the exporter's dptr
+ *   ipc_close  : unmaps (pass the pointer ipc_open returned)
+ *   copy_async : device-to-device copy on `stream`, local or peer source (cudaMemcpyAsync; no kernel is launched) */
+int jblas_b200_ipc_export(const void* dptr, void* handle64, int64_t* offset);
+int jblas_b200_ipc_open(const void* handle64, int64_t offset, void** peer_ptr);
+int jblas_b200_ipc_close(void* peer_ptr);
+int jblas_b200_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+
 /* ---- inputs: mrandn (src/randmat.jl:5-14): iid N(0,1) fill, here counter-based and seeded -----------
  * Writes elements [first, first+n) of the stream keyed by `seed` to dptr[0..n): element e depends only on
  * (seed, e), so a column shard of a matrix (first = col0*rows) holds the same values as the whole matrix. */

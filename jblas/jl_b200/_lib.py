@@ -57,6 +57,10 @@ PROTOTYPES = {
     "jblas_b200_host_register": (c_int, [c_vp, ctypes.c_size_t]),
     "jblas_b200_host_unregister": (c_int, [c_vp]),
     "jblas_b200_stream_sync": (c_int, [c_vp]),
+    "jblas_b200_ipc_export": (c_int, [c_vp, c_vp, ctypes.POINTER(c_i64)]),
+    "jblas_b200_ipc_open": (c_int, [c_vp, c_i64, ctypes.POINTER(c_vp)]),
+    "jblas_b200_ipc_close": (c_int, [c_vp]),
+    "jblas_b200_copy_async": (c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "jblas_b200_randn_fill": (c_int, [c_vp, c_i64, c_i64, ctypes.c_uint64, c_int, c_vp]),
     "jblas_b200_plan": (c_int, [c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, ctypes.POINTER(c_i64)]),
     "jblas_b200_num_kernels": (c_int, []),

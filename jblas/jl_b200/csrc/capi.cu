@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1331,6 +1332,69 @@ int jblas_b200_stream_sync(void* stream)
 {
     if (int rc = require_init()) return rc;
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+// ---- peer memory (CUDA IPC) ----
+static std::map<void*, void*> g_ipc_maps;  // pointer handed to the caller -> base of the mapping
+
+int jblas_b200_ipc_export(const void* dptr, void* handle64, int64_t* offset)
+{
+    if (int rc = require_init()) return rc;
+    if (!dptr || !handle64 || !offset) return fail(JBLAS_B200_EINVAL, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    // cudaIpcGetMemHandle names the whole ALLOCATION dptr lies in (a caching allocator may have carved dptr out of a larger
+    // block), so the offset of dptr inside it travels with the handle
+    typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static GetRangeFn get_range = nullptr;
+    if (!get_range) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(JBLAS_B200_ECUDA, "cuMemGetAddressRange is not available from this driver");
+        get_range = (GetRangeFn)fn;
+    }
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    CUresult r = get_range(&base, &size, (CUdeviceptr)dptr);
+    if (r != CUDA_SUCCESS) return fail(JBLAS_B200_ECUDA, "cuMemGetAddressRange failed with CUresult %d", (int)r);
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, (void*)base));
+    memcpy(handle64, &h, 64);
+    *offset = (int64_t)((CUdeviceptr)dptr - base);
+    return 0;
+}
+int jblas_b200_ipc_open(const void* handle64, int64_t offset, void** peer_ptr)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = require_init()) return rc;
+    if (!handle64 || !peer_ptr || offset < 0) return fail(JBLAS_B200_EINVAL, "bad ipc_open arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* base = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *peer_ptr = (char*)base + offset;
+    g_ipc_maps[*peer_ptr] = base;
+    return 0;
+}
+int jblas_b200_ipc_close(void* peer_ptr)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = require_init()) return rc;
+    auto it = g_ipc_maps.find(peer_ptr);
+    if (it == g_ipc_maps.end()) return fail(JBLAS_B200_EINVAL, "pointer was not returned by jblas_b200_ipc_open");
+    void* base = it->second;
+    g_ipc_maps.erase(it);
+    CUDA_TRY(cudaIpcCloseMemHandle(base));
+    return 0;
+}
+int jblas_b200_copy_async(void* dst, const void* src, size_t bytes, void* stream)
+{
+    if (int rc = require_init()) return rc;
+    if (bytes == 0) return 0;
+    if (!dst || !src) return fail(JBLAS_B200_EINVAL, "NULL pointer");
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 

@@ -11,6 +11,15 @@ M*(k1-k0) block) on the NCCL stream while the local GEMM consumes earlier panels
     panel p arrives  ->  D_shard (+)= A[:, kp] * X_shard[kp, :]      accumulate = (p > 0)
 The accumulate pass has the reference's kernel! semantics (src/kernels.jl:226): each element's chain stays
 ascending in k across panels, so an N-GPU result is bit-identical to the 1-GPU result with the exact kernels.
+
+Two transports for the exchange step (`bcast=`):
+  "nccl" : torch.distributed.broadcast per panel.  NCCL's kernels need SMs; the persistent GEMM CTAs fill every SM, so the
+           two compete (8 GPUs, 32768^3: ~5 % of the step).
+  "p2p"  : the owner exports its A allocation over CUDA IPC once (jblas_b200_ipc_export), every other rank maps it and PULLS
+           the K panels with the copy engines over NVLink (jblas_b200_copy_async on the communication stream) -- no kernel,
+           no SM.  Two tiny all-reduces per call (20 us each, on the compute stream, outside the multiplies) fence the owner's
+           buffer: one before the pulls (A is final), one at the end (A may be overwritten once the call returns).  The owner
+           multiplies with one full-K launch.
 """
 from __future__ import annotations
 
@@ -62,7 +71,8 @@ class ShardedGemm:
     """
 
     def __init__(self, M: int, K: int, n_cols_total: int, group=None, root: int = 0, panel_k: int = 2048,
-                 kernel: Optional[int] = None, local_gemm: Optional[Callable] = None, first_panel_k: Optional[int] = None):
+                 kernel: Optional[int] = None, local_gemm: Optional[Callable] = None, first_panel_k: Optional[int] = None,
+                 bcast: str = "nccl"):
         import torch.distributed as dist
 
         self.dist = dist
@@ -76,6 +86,86 @@ class ShardedGemm:
         self.kernel = kernel
         self.local_gemm = local_gemm or _default_local_gemm
         self._comm_stream = None
+        if bcast not in ("nccl", "p2p"):
+            raise ValueError("bcast must be 'nccl' or 'p2p'")
+        self.bcast = bcast
+        self._peer = {}    # local A buffer address -> address of the owner's A as mapped into this process
+        self._fence = None
+
+    def _owner_ptr(self, A):
+        """Address of the owner's A in THIS process: CUDA IPC mapping, established once per A buffer (collective call).
+        The owner's and the peers' A buffers must stay the same allocations for the life of this object."""
+        key = A.data_ptr()
+        if key in self._peer:
+            return self._peer[key]
+        import ctypes
+        import struct
+
+        import torch
+
+        from . import _lib
+
+        L = _lib.lib()
+        wire = torch.zeros(72, dtype=torch.uint8, device=A.device)
+        if self.rank == self.root:
+            handle, off = (ctypes.c_ubyte * 64)(), ctypes.c_int64()
+            _lib.check(L.jblas_b200_ipc_export(A.data_ptr(), handle, ctypes.byref(off)))
+            wire.copy_(torch.frombuffer(bytearray(bytes(handle) + struct.pack("<q", off.value)), dtype=torch.uint8))
+        self.dist.broadcast(wire, src=self.root, group=self.group)
+        if self.rank == self.root:
+            ptr = A.data_ptr()
+        else:
+            raw = bytes(wire.cpu().numpy().tobytes())
+            handle = (ctypes.c_ubyte * 64).from_buffer_copy(raw[:64])
+            mapped = ctypes.c_void_p()
+            _lib.check(L.jblas_b200_ipc_open(handle, struct.unpack("<q", raw[64:72])[0], ctypes.byref(mapped)))
+            ptr = mapped.value
+        self._peer[key] = ptr
+        return ptr
+
+    def close(self):
+        """Unmap the owner's buffers (peers only)."""
+        if self.rank != self.root and self._peer:
+            from . import _lib
+
+            for ptr in self._peer.values():
+                _lib.lib().jblas_b200_ipc_close(ptr)
+        self._peer = {}
+
+    def _call_p2p(self, D_shard, A, X_shard):
+        import torch
+
+        from . import _lib
+
+        L = _lib.lib()
+        dev = A.device
+        owner = self._owner_ptr(A)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=dev)
+        if self._fence is None:
+            self._fence = torch.zeros(1, dtype=torch.int32, device=dev)
+        compute, comm = torch.cuda.current_stream(dev), self._comm_stream
+        es = A.element_size()
+        # Both fences run on the COMPUTE stream, i.e. strictly between GEMM launches: a fence kernel that waited for a slow peer
+        # while this rank's persistent GEMM CTAs fill every SM would either starve or hold an SM the next launch needs
+        # (measured: +3 ms per step when the second fence overlapped the multiplies).
+        self.dist.all_reduce(self._fence, group=self.group)  # fence 1: the owner's A is final, every receive buffer is free
+        ready = []
+        if self.rank != self.root:
+            comm.wait_stream(compute)
+            for k0, k1 in self.panels:  # a K panel of a dense column-major matrix is one contiguous block
+                _lib.check(L.jblas_b200_copy_async(A.data_ptr() + k0 * self.M * es, owner + k0 * self.M * es,
+                                                   (k1 - k0) * self.M * es, comm.cuda_stream))
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                ready.append(ev)
+            for p, (k0, k1) in enumerate(self.panels):
+                compute.wait_event(ready[p])
+                self.local_gemm(D_shard, self._panel(A, k0, k1), X_shard[k0:k1, :], p > 0, self.kernel)
+        else:
+            self.local_gemm(D_shard, A, X_shard, False, self.kernel)  # A is local: one full-K launch
+        self.dist.all_reduce(self._fence, group=self.group)  # fence 2: every rank holds its copy; the owner may rewrite A
+        return D_shard
 
     @property
     def shard_cols(self) -> int:
@@ -102,6 +192,8 @@ class ShardedGemm:
         if not A.t().is_contiguous():
             raise ValueError("A must be dense column-major (leading dimension == M) to be broadcast in K panels")
         cuda = A.is_cuda
+        if cuda and self.bcast == "p2p":
+            return self._call_p2p(D_shard, A, X_shard)
         works = []
         if cuda:
             if self._comm_stream is None:

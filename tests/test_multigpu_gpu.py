@@ -45,6 +45,20 @@ def _worker(rank, world, port, M, K, N, panel_k, out_dir):
             torch.cuda.synchronize()
             assert not torch.isnan(A).any() and not torch.isnan(D).any()
             res[tag] = D.cpu().numpy()
+            # the copy-engine transport: the owner's A is mapped over CUDA IPC and pulled in K panels, no NCCL data path
+            sgp = ShardedGemm(M, K, N, panel_k=panel_k, kernel=sel, bcast="p2p")
+            Ap = jb.mrandn(M, K, seed=11) if rank == 0 else jb.empty_colmajor(M, K, fill=float("nan"))
+            Dp = jb.empty_colmajor(M, sg.shard_cols, fill=float("nan"))
+            for _ in range(2):
+                sgp(Dp, Ap, X)
+            torch.cuda.synchronize()
+            assert not torch.isnan(Ap).any() and np.array_equal(Dp.cpu().numpy(), res[tag]), f"p2p transport differs ({tag})"
+            if rank == 0:
+                Ap.mul_(2.0)  # the owner rewrites A in place between calls: the fences must order it against the peers' pulls
+            sgp(Dp, Ap, X)
+            torch.cuda.synchronize()
+            assert np.array_equal(Dp.cpu().numpy(), 2.0 * res[tag]), f"p2p transport: stale A after an in-place update ({tag})"
+            sgp.close()
             # host-facing pipelined form: pinned host shards in, pinned host shard out, same bits
             Xh = torch.empty((sg.shard_cols, K), dtype=torch.float64).pin_memory()
             Xh.copy_(X.t())

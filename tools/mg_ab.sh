@@ -1,6 +1,12 @@
-run() { tag=$1; shift; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --no-e2e $EXTRA > gpurun_out/mg_$tag.json 2> gpurun_out/mg_$tag.err; python -c "import json;d=json.load(open('gpurun_out/mg_$tag.json'));print('$tag', d['ms_per_step'], d['value'], d['config']['parallelism'])"; }
-EXTRA="" run dyn A=1
-EXTRA="" run static JBLAS_B200_STATIC_TILES=1
-EXTRA="--first-panel-k 0" run dyn_nofirst A=1
-EXTRA="--first-panel-k 0" run static_nofirst JBLAS_B200_STATIC_TILES=1
-EXTRA="" run dyn2 A=1
+#!/bin/bash
+# N-GPU A/B of the two A transports (multigpu.py): NCCL broadcast vs CUDA-IPC copy-engine pulls
+N=${1:-2}
+run() { tag=$1; shift; timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --warmup 3 --no-e2e "$@" > gpurun_out/mg_$tag.json 2> gpurun_out/mg_$tag.err; python -c "import json;d=json.load(open('gpurun_out/mg_$tag.json'));print('$tag', round(d['ms_per_step'],3), round(d['value'],2), d['config']['parallelism'])" || tail -5 gpurun_out/mg_$tag.err; }
+run nccl --steps 10
+run p2p --steps 10 --bcast p2p
+run nccl2 --steps 10
+run p2p2 --steps 10 --bcast p2p
+if [ "${2:-}" = "c5" ]; then
+run c5_nccl --workload c5 --steps 3
+run c5_p2p --workload c5 --steps 3 --bcast p2p
+fi
