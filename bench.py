@@ -477,7 +477,7 @@ def run_gpu(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic N(0,1), device-generated Philox (mrandn analogue), seeds jBLA/jBLA+1",
             "config": {"workload": desc, "M": M, "K": K, "N_total": n_total, "N_per_gpu": sg.shard_cols, "kernel_selector": args.kernel,
-                       "parallelism": f"column-shard x{world}" + (f", A broadcast ({args.bcast}) in {len(sg.panels)} K-panels (first {sg.panels[0][1] - sg.panels[0][0]}, then {args.panel_k})" if world > 1 else ""),
+                       "parallelism": f"column-shard x{world}" + (f", A broadcast ({sg.bcast}) in {len(sg.panels)} K-panels (first {sg.panels[0][1] - sg.panels[0][0]}, then {args.panel_k})" if world > 1 else ""),
                        "l2": f"inputs larger than L2: A+X+D = {(M * K + K * sg.shard_cols + M * sg.shard_cols) * es / 2**20:.0f} MiB per GPU vs 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -561,7 +561,8 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "dmma", "simt", "tf32x3"])
     ap.add_argument("--panel-k", type=int, default=2048)
     ap.add_argument("--first-panel-k", type=int, default=256, help="shorter first K panel of the A broadcast (0 = same as the others)")
-    ap.add_argument("--bcast", default="nccl", choices=["nccl", "p2p"], help="N > 1: how A reaches the other GPUs (multigpu.py)")
+    ap.add_argument("--bcast", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="N > 1: how A reaches the other GPUs (multigpu.py); auto = copy-engine pulls over CUDA IPC if every rank can map A, else NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large workloads)")
     args = ap.parse_args()

@@ -86,8 +86,8 @@ class ShardedGemm:
         self.kernel = kernel
         self.local_gemm = local_gemm or _default_local_gemm
         self._comm_stream = None
-        if bcast not in ("nccl", "p2p"):
-            raise ValueError("bcast must be 'nccl' or 'p2p'")
+        if bcast not in ("nccl", "p2p", "auto"):
+            raise ValueError("bcast must be 'nccl', 'p2p' or 'auto' (p2p when the CUDA IPC mapping succeeds on every rank)")
         self.bcast = bcast
         self._peer = {}    # local A buffer address -> address of the owner's A as mapped into this process
         self._fence = None
@@ -106,20 +106,35 @@ class ShardedGemm:
         from . import _lib
 
         L = _lib.lib()
-        wire = torch.zeros(72, dtype=torch.uint8, device=A.device)
+        wire = torch.zeros(73, dtype=torch.uint8, device=A.device)  # handle (64) | offset (8) | export succeeded (1)
+        err = None
         if self.rank == self.root:
             handle, off = (ctypes.c_ubyte * 64)(), ctypes.c_int64()
-            _lib.check(L.jblas_b200_ipc_export(A.data_ptr(), handle, ctypes.byref(off)))
-            wire.copy_(torch.frombuffer(bytearray(bytes(handle) + struct.pack("<q", off.value)), dtype=torch.uint8))
+            try:
+                _lib.check(L.jblas_b200_ipc_export(A.data_ptr(), handle, ctypes.byref(off)))
+                wire.copy_(torch.frombuffer(bytearray(bytes(handle) + struct.pack("<q", off.value) + b"\x01"), dtype=torch.uint8))
+            except Exception as e:  # noqa: BLE001 -- reported to every rank below; the collective sequence must stay aligned
+                err = e
         self.dist.broadcast(wire, src=self.root, group=self.group)
-        if self.rank == self.root:
-            ptr = A.data_ptr()
-        else:
+        ptr = A.data_ptr()
+        if self.rank != self.root:
             raw = bytes(wire.cpu().numpy().tobytes())
-            handle = (ctypes.c_ubyte * 64).from_buffer_copy(raw[:64])
-            mapped = ctypes.c_void_p()
-            _lib.check(L.jblas_b200_ipc_open(handle, struct.unpack("<q", raw[64:72])[0], ctypes.byref(mapped)))
-            ptr = mapped.value
+            if raw[72] != 1:
+                err = RuntimeError("the owner could not export its A allocation over CUDA IPC")
+            else:
+                handle = (ctypes.c_ubyte * 64).from_buffer_copy(raw[:64])
+                mapped = ctypes.c_void_p()
+                try:
+                    _lib.check(L.jblas_b200_ipc_open(handle, struct.unpack("<q", raw[64:72])[0], ctypes.byref(mapped)))
+                    ptr = mapped.value
+                except Exception as e:  # noqa: BLE001
+                    err = e
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=A.device)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)  # every rank learns whether ALL mappings exist
+        if int(ok.item()) != 1:
+            if err is None and self.rank != self.root and ptr != A.data_ptr():
+                L.jblas_b200_ipc_close(ptr)
+            raise RuntimeError(f"CUDA IPC mapping of the owner's A failed on at least one rank ({err})")
         self._peer[key] = ptr
         return ptr
 
@@ -192,6 +207,12 @@ class ShardedGemm:
         if not A.t().is_contiguous():
             raise ValueError("A must be dense column-major (leading dimension == M) to be broadcast in K panels")
         cuda = A.is_cuda
+        if cuda and self.bcast == "auto":  # collective decision, taken once: p2p if every rank can map the owner's A
+            try:
+                self._owner_ptr(A)
+                self.bcast = "p2p"
+            except RuntimeError:
+                self.bcast = "nccl"
         if cuda and self.bcast == "p2p":
             return self._call_p2p(D_shard, A, X_shard)
         works = []

@@ -59,6 +59,13 @@ def _worker(rank, world, port, M, K, N, panel_k, out_dir):
             torch.cuda.synchronize()
             assert np.array_equal(Dp.cpu().numpy(), 2.0 * res[tag]), f"p2p transport: stale A after an in-place update ({tag})"
             sgp.close()
+            sga = ShardedGemm(M, K, N, panel_k=panel_k, kernel=sel, bcast="auto")  # collective choice, made at the first call
+            if rank == 0:
+                Ap.mul_(0.5)
+            sga(Dp, Ap, X)
+            torch.cuda.synchronize()
+            assert sga.bcast in ("p2p", "nccl") and np.array_equal(Dp.cpu().numpy(), res[tag]), f"auto transport ({sga.bcast}, {tag})"
+            sga.close()
             # host-facing pipelined form: pinned host shards in, pinned host shard out, same bits
             Xh = torch.empty((sg.shard_cols, K), dtype=torch.float64).pin_memory()
             Xh.copy_(X.t())
