@@ -1145,9 +1145,10 @@ static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t 
             const int64_t warps_needed = tiny ? (batch + 3) / 4 : batch * mblocks * pblocks;
             int64_t grid = (int64_t)g_ctx.num_sms * 16;  // 128-thread CTAs; the hardware keeps as many resident as registers allow
             if (grid * 4 > warps_needed) grid = (warps_needed + 3) / 4;
-#define BATCHED_DMMA(MI_, NI_, KC_, U_)                                                                                              \
-    fastmul_batched_dmma_kernel<MI_, NI_, KC_, U_><<<(unsigned)grid, 128, 0, s>>>(                                                     \
+#define BATCHED_DMMA_LAUNCH(MI_, NI_, KC_, U_, ONE_)                                                                                 \
+    fastmul_batched_dmma_kernel<MI_, NI_, KC_, U_, ONE_><<<(unsigned)grid, 128, 0, s>>>(                                               \
         (double*)D, (const double*)A, (const double*)X, (int)M, (int)N, (int)P, batch, strideD, strideA, strideX, mblocks, pblocks)
+#define BATCHED_DMMA(MI_, NI_, KC_, U_) BATCHED_DMMA_LAUNCH(MI_, NI_, KC_, U_, true)
 #define BATCHED_DMMA_ROW(MI_)                                                                                                        \
     switch (ni) {                                                                                                                    \
         case 1: BATCHED_DMMA(MI_, 1, ((MI_) + 1 <= 4 ? 8 : 4), 1); break;                                                            \
@@ -1157,6 +1158,8 @@ static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t 
     }
             if (tiny) {
                 BATCHED_DMMA(1, 1, 2, 4);
+            } else if (!one_block) {
+                BATCHED_DMMA_LAUNCH(4, 4, 4, 1, false);
             } else {
                 switch (mi) {
                     case 1: BATCHED_DMMA_ROW(1) break;
@@ -1167,6 +1170,7 @@ static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t 
             }
 #undef BATCHED_DMMA_ROW
 #undef BATCHED_DMMA
+#undef BATCHED_DMMA_LAUNCH
             g_launches++;
             CUDA_TRY(cudaGetLastError());
             return 0;

@@ -131,7 +131,7 @@ fastmul_batched_kernel(T* __restrict__ D, const T* __restrict__ A, const T* __re
 // Larger products (M or P > 32) are cut into 32 x 32 blocks of D, one warp each; the warps of one product run side by side,
 // so the A row-block / X column-block a sibling already fetched comes from L1/L2.  Tiny products (M, P <= 8, N <= 16) move
 // too few bytes per warp to cover the HBM latency, so a warp takes U = 4 consecutive products per iteration.
-template <int MI, int NI, int KC, int U>
+template <int MI, int NI, int KC, int U, bool ONE_BLOCK>
 __global__ void __launch_bounds__(128, (MI * NI >= 12 ? 3 : (U > 1 ? 6 : 1)))  // 3 CTAs/SM = 170 registers: the 4x4 grid otherwise takes 186
                                                                                // and drops to 2; the tiny-product variant is latency-bound:
                                                                                // 6 CTAs/SM (ncu: 152 registers, 17 % warps active without)
@@ -140,7 +140,7 @@ fastmul_batched_dmma_kernel(double* __restrict__ D, const double* __restrict__ A
 {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int nblk = mblocks * pblocks;
+    const int nblk = ONE_BLOCK ? 1 : mblocks * pblocks;  // ONE_BLOCK (M, P <= 32): no 64-bit division per product
     const int64_t items = (batch * nblk + U - 1) / U;  // a work item = U consecutive (product, block) pairs
     for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < items; item += nwarps) {
         const double* __restrict__ a[U];
@@ -152,10 +152,15 @@ fastmul_batched_dmma_kernel(double* __restrict__ D, const double* __restrict__ A
         for (int u = 0; u < U; ++u) {
             const int64_t w = item * U + u;
             live[u] = w < batch * nblk;
-            prod[u] = live[u] ? w / nblk : 0;
-            const int blk = live[u] ? (int)(w - prod[u] * nblk) : 0;
-            r0[u] = (blk % mblocks) * 32;
-            c0[u] = (blk / mblocks) * 32;
+            if constexpr (ONE_BLOCK) {
+                prod[u] = live[u] ? w : 0;
+                r0[u] = c0[u] = 0;
+            } else {
+                prod[u] = live[u] ? w / nblk : 0;
+                const int blk = live[u] ? (int)(w - prod[u] * nblk) : 0;
+                r0[u] = (blk % mblocks) * 32;
+                c0[u] = (blk / mblocks) * 32;
+            }
             a[u] = A + prod[u] * strideA;
             x[u] = X + prod[u] * strideX;
         }
