@@ -105,6 +105,30 @@ def test_no_cpu_fallback_without_gpu(jb):
     assert L.jblas_b200_gemm_f64_dev(1, 1, 1, 4, 3, 5, 4, 4, 3, 0, 0, None) == -3  # ENOTINIT
     assert b"no CPU fallback" in L.jblas_b200_last_error()
     assert L.jblas_b200_jmul_f64(D.ctypes.data, A.ctypes.data, X.ctypes.data, 4, 3, 5) == -3
+    # the newer entries fail the same way: fused forms, batched fastmul! (host and device), peer memory
+    C = np.ones((4, 5), order="F")
+    for fn in (jb.gemm_plus_c_, jb.gemm_x_plus_c_):
+        with pytest.raises(jb.JblasB200Error):
+            fn(D, A, X, C if fn is jb.gemm_plus_c_ else np.ones((3, 5), order="F"))
+    bA, bX = np.ones((2, 3, 4)).transpose(0, 2, 1), np.ones((2, 5, 3)).transpose(0, 2, 1)
+    bD = np.full((2, 5, 4), np.nan).transpose(0, 2, 1)
+    with pytest.raises(jb.JblasB200Error):
+        jb.fastmul_batched_(bD, bA, bX)
+    assert np.isnan(D).all() and np.isnan(bD).all()
+    assert L.jblas_b200_fastmul_batched_f64_dev(1, 1, 1, 4, 3, 5, 2, 20, 12, 15, None) == -3
+    assert L.jblas_b200_copy_async(1, 1, 8, None) == -3
+    import ctypes
+
+    off = ctypes.c_int64()
+    assert L.jblas_b200_ipc_export(1, (ctypes.c_ubyte * 64)(), ctypes.byref(off)) == -3
+
+
+def test_multigpu_transport_argument_is_validated():
+    from jblas.jl_b200.multigpu import ShardedGemm
+
+    with pytest.raises(ValueError):
+        ShardedGemm(8, 8, 8, bcast="rdma")
+    assert ShardedGemm(8, 8, 8, bcast="auto").bcast == "auto"  # decided collectively at the first GPU call
 
 
 def test_product_never_imports_the_oracle():
