@@ -801,8 +801,28 @@ static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t
         int64_t nb = (int64_t)(panel_bytes / ((size_t)M * es));
         nb = nb / 128 * 128;
         if (nb < 128) nb = 128;
+        // Panel ramp.  Panel i+1 is uploaded while panel i is multiplied, so without a bubble it can exceed panel i only by the
+        // ratio of the two rates in contraction columns per second: H2D moves (M + N1) elements per column, the multiply
+        // spends 2*M*N1 flops on it.  8192^3 f64: 573 vs 515 columns per ms -> x1.11 per step (a fixed 256 -> 1024 jump left the
+        // tensor pipe idle for 1.3 ms at the start, JBLAS_B200_TRACE timeline).
+        double growth = 0.0;
+        if (big && kfirst < kp) {
+            const double h2d_bytes_per_s = 55e9;  // measured, pinned host memory
+            // sustained rates of the ACCUMULATE passes (a pass re-reads its D tiles): 34.5 of the 36 TFLOP/s in f64
+            const double flops_per_s = dtype == JBLAS_B200_DT_F64 ? 34.5e12 : (selector == JBLAS_B200_F32_3XTF32 ? 230e12 : 52e12);
+            growth = (h2d_bytes_per_s / ((double)(M + N1) * es)) / (flops_per_s / (2.0 * (double)M * (double)N1));
+            if (growth > 2.0) growth = 2.0;
+            if (growth < 1.02) growth = 0.0;  // copy-bound: nothing to gain, keep the two-size scheme
+        }
+        double ramp = (double)kfirst;
         for (int64_t k0 = 0; k0 < K;) {
-            const int64_t kstep = (k0 == 0) ? kfirst : kp;
+            int64_t kstep = (k0 == 0) ? kfirst : kp;
+            if (growth > 0.0 && k0 > 0) {
+                ramp *= growth;
+                kstep = ((int64_t)(ramp / 64.0 + 0.5)) * 64;
+                if (kstep < kfirst) kstep = kfirst;
+                if (kstep > kp) kstep = kp;
+            }
             const int64_t kc = (K - k0 < kstep) ? (K - k0) : kstep;
             const int acc = (accumulate || k0 > 0) ? 1 : 0;
             CUDA_TRY(cudaMemcpy2DAsync(dA + k0 * dM, dM * es, A + k0 * lda, lda * es, M * es, kc, cudaMemcpyHostToDevice, cs));
