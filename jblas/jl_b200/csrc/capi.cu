@@ -1196,6 +1196,58 @@ static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t 
             return 0;
         }
     }
+    if constexpr (sizeof(T) == 4) {
+        // Float32 up to 32 x N x 16 (even M, N % 4 == 0, 16-byte aligned): warp-private staging, FFMA2, no CTA barriers
+        static int force_generic = -1;
+        if (force_generic < 0) {
+            const char* e = getenv("JBLAS_B200_BATCHED_SIMT");
+            force_generic = (e && atoi(e)) ? 1 : 0;
+        }
+        const bool ok = !force_generic && M % 2 == 0 && M <= 32 && P <= 16 && N % 4 == 0 && strideA % 4 == 0 && strideX % 4 == 0 &&
+                        strideD % 2 == 0 && is_aligned16(A) && is_aligned16(X) && ((reinterpret_cast<uintptr_t>(D) & 7) == 0);
+        if (ok) {
+            const int lpp = M <= 16 ? 8 : 16, ppw = 32 / lpp, pc = (int)((P + 1) / 2 * 2);
+            const int slot_floats = (int)(((M * N + N * pc) + 31) / 32 * 32 + 16);  // +16: the two products of a half-warp in different banks
+            const int warps_per_cta = 2;
+            const size_t smem = (size_t)warps_per_cta * 2 * ppw * slot_floats * sizeof(float) + (size_t)warps_per_cta * 2 * sizeof(uint64_t);
+            if (smem <= (size_t)200 * 1024) {
+                int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
+                if (per_sm < 1) per_sm = 1;
+                if (per_sm > 8) per_sm = 8;
+                const int64_t items = (batch + ppw - 1) / ppw;
+                int64_t grid = (int64_t)g_ctx.num_sms * per_sm;
+                if (grid * warps_per_cta > items) grid = (items + warps_per_cta - 1) / warps_per_cta;
+#define F32_WARP(LPP_, PC_)                                                                                                           \
+    {                                                                                                                                 \
+        static bool attr_done = false;                                                                                               \
+        if (!attr_done) {                                                                                                            \
+            CUDA_TRY(cudaFuncSetAttribute(fastmul_batched_f32_warp_kernel<LPP_, PC_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                          (int)(200 * 1024)));                                                                      \
+            attr_done = true;                                                                                                        \
+        }                                                                                                                            \
+        fastmul_batched_f32_warp_kernel<LPP_, PC_><<<(unsigned)grid, 32 * warps_per_cta, smem, s>>>(                                  \
+            (float*)D, (const float*)A, (const float*)X, (int)M, (int)N, (int)P, batch, strideD, strideA, strideX, slot_floats);     \
+    }
+#define F32_WARP_PC(LPP_)                                                                                                             \
+    switch (pc) {                                                                                                                    \
+        case 2: F32_WARP(LPP_, 2) break;                                                                                             \
+        case 4: F32_WARP(LPP_, 4) break;                                                                                             \
+        case 6: F32_WARP(LPP_, 6) break;                                                                                             \
+        case 8: F32_WARP(LPP_, 8) break;                                                                                             \
+        case 10: F32_WARP(LPP_, 10) break;                                                                                           \
+        case 12: F32_WARP(LPP_, 12) break;                                                                                           \
+        case 14: F32_WARP(LPP_, 14) break;                                                                                           \
+        default: F32_WARP(LPP_, 16) break;                                                                                           \
+    }
+                if (lpp == 8) { F32_WARP_PC(8) } else { F32_WARP_PC(16) }
+#undef F32_WARP_PC
+#undef F32_WARP
+                g_launches++;
+                CUDA_TRY(cudaGetLastError());
+                return 0;
+            }
+        }
+    }
     const int xpitch = (int)(N | 1);  // odd column pitch: the column lanes of a warp hit distinct banks
     const size_t slot = ((((size_t)M * N + (size_t)xpitch * P) + 1) & ~(size_t)1) * sizeof(T);  // even element count, as in the kernel
     if (2 * slot > (size_t)200 * 1024)

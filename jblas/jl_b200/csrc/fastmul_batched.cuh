@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm_dmma.cuh"
+#include "gemm_dmma_tma.cuh"
 
 namespace jb {
 
@@ -220,6 +221,104 @@ fastmul_batched_dmma_kernel(double* __restrict__ D, const double* __restrict__ A
                     }
                 }
         }
+    }
+}
+
+// ---- Float32, products up to 32 x N x 16: FFMA2 with warp-private staging -----------------------------------------------------
+// There is no exact FP32 tensor path, and the generic kernel above is bound by its shared-memory traffic and CTA barriers
+// (16x32x14: 2.0 TB/s, 31 % of HBM).  Here LPP = 8 (M <= 16) or 16 (M <= 32) lanes own one product, so a warp multiplies 4 or 2
+// products side by side with NO CTA-wide synchronisation: each warp double-buffers its own products in shared memory with TMA bulk
+// copies (cp.async.bulk, one per matrix: A and X exactly as they lie in HBM, no transposition; one lane issues them, an mbarrier
+// per stage counts the bytes) and synchronises with __syncwarp only.  (A first version staged with per-lane 16-byte cp.async:
+// 4.1 TB/s -- the copies, not HBM, were the limit.)
+//   lane l of a product holds rows (2l, 2l+1) of ALL columns: PC packed accumulators (fma.rn.f32x2: one instruction = both rows);
+//   per 4 k:  4 LDS.64 (its two rows of A[:, k..k+3]) + PC LDS.128 (X[k..k+3, c], the same address for the whole product =
+//             broadcast) feed 4*PC FFMA2 -- 18 loads per 56 FFMA2 for P = 14, against 3 loads per 4 FMAs above;
+//   product slots are skewed by 16 floats so the two products of a half-warp sit in different banks.
+// Every element is the reference chain (ascending k, start -0.0): bit-identical to the oracle.
+// Preconditions (checked by the host): M even, N % 4 == 0, strides % 4 == 0, 16-byte aligned bases.
+template <int LPP, int PC>
+__global__ void __launch_bounds__(64)
+fastmul_batched_f32_warp_kernel(float* __restrict__ D, const float* __restrict__ A, const float* __restrict__ X, int M, int N, int P,
+                                int64_t batch, int64_t strideD, int64_t strideA, int64_t strideX, int slot_floats)
+{
+    constexpr int PPW = 32 / LPP;  // products per warp
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+    const int q = lane / LPP, l = lane % LPP;
+    float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * PPW * slot_floats;  // [stage][slot][A | X]
+    const int a_floats = M * N, x_floats = N * P;
+    const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
+    const int64_t items = (batch + PPW - 1) / PPW;
+    // one mbarrier per (warp, stage), after the data of all warps
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + (size_t)warps_per_cta * 2 * PPW * slot_floats) + warp * 2;
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto load = [&](int64_t item, int stage) {  // lane 0: arm the stage's barrier with the byte count, then one bulk copy per matrix
+        if (lane != 0) return;
+        float* st = wbase + (size_t)stage * PPW * slot_floats;
+        const int64_t b0 = item * PPW;
+        const int live = (int)min((int64_t)PPW, batch - b0);
+        mbar_expect_tx(&bars[stage], (uint32_t)(live * (a_floats + x_floats) * 4));
+        for (int pq = 0; pq < live; ++pq) {
+            float* sp = st + pq * slot_floats;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(sp)),
+                         "l"(A + (b0 + pq) * strideA), "r"(a_floats * 4), "r"(smem_u32(&bars[stage]))
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                             smem_u32(sp + a_floats)),
+                         "l"(X + (b0 + pq) * strideX), "r"(x_floats * 4), "r"(smem_u32(&bars[stage]))
+                         : "memory");
+        }
+    };
+
+    int64_t item = (int64_t)blockIdx.x * warps_per_cta + warp;
+    if (item < items) load(item, 0);
+    int stage = 0;
+    uint32_t parity = 0;  // bit s = phase parity of stage s
+    for (; item < items; item += nwarps, stage ^= 1) {
+        const int64_t nxt = item + nwarps;
+        if (nxt < items) load(nxt, stage ^ 1);
+        mbar_wait(&bars[stage], (parity >> stage) & 1u);
+        parity ^= 1u << stage;
+        const float* sa = wbase + ((size_t)stage * PPW + q) * slot_floats;
+        const float* sx = sa + a_floats;
+        const int r0 = min(2 * l, M - 2);  // lanes beyond the last row pair recompute it (never stored): no out-of-slot reads
+        uint64_t acc[PC];
+#pragma unroll
+        for (int c = 0; c < PC; ++c) acc[c] = 0x8000000080000000ull;  // (-0.0f, -0.0f): fma(a, b, -0) == a*b
+#pragma unroll 2
+        for (int k = 0; k < N; k += 4) {
+            uint64_t a[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) a[kk] = *reinterpret_cast<const uint64_t*>(sa + (k + kk) * M + r0);
+#pragma unroll
+            for (int c = 0; c < PC; ++c) {
+                const float4 xv = *reinterpret_cast<const float4*>(sx + c * N + k);
+                uint64_t b0, b1, b2, b3;
+                asm("mov.b64 %0, {%1, %1};\n" : "=l"(b0) : "f"(xv.x));
+                asm("mov.b64 %0, {%1, %1};\n" : "=l"(b1) : "f"(xv.y));
+                asm("mov.b64 %0, {%1, %1};\n" : "=l"(b2) : "f"(xv.z));
+                asm("mov.b64 %0, {%1, %1};\n" : "=l"(b3) : "f"(xv.w));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(acc[c]) : "l"(a[0]), "l"(b0));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(acc[c]) : "l"(a[1]), "l"(b1));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(acc[c]) : "l"(a[2]), "l"(b2));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;\n" : "+l"(acc[c]) : "l"(a[3]), "l"(b3));
+            }
+        }
+        const int64_t b = item * PPW + q;
+        if (b < batch && 2 * l < M) {  // M is even: rows r0, r0+1 exist together
+            float* dp = D + b * strideD + r0;
+#pragma unroll
+            for (int c = 0; c < PC; ++c)
+                if (c < P) *reinterpret_cast<uint64_t*>(dp + (size_t)c * M) = acc[c];
+        }
+        __syncwarp();  // every lane is done with this stage before lane 0 lets the next bulk copies overwrite it
     }
 }
 

@@ -13,7 +13,10 @@ pytestmark = pytest.mark.gpu
 #   everything else the shared-memory SIMT kernel
 SHAPES = [(16, 32, 14), (32, 32, 6), (32, 32, 24), (1, 1, 1), (5, 3, 7), (13, 40, 5), (40, 8, 5), (64, 64, 64), (3, 100, 2), (97, 11, 33),
           (25, 7, 31), (32, 70, 32), (8, 4, 8), (24, 33, 9), (9, 17, 24), (8, 16, 8), (20, 10, 130), (128, 5, 100),
-          (96, 34, 70), (130, 6, 40), (66, 130, 34)]  # Float64, even M and N, M or P > 32: the TMA/DMMA GEMM kernel over 3-D tensor maps
+          (96, 34, 70), (130, 6, 40), (66, 130, 34),  # Float64, even M and N, M or P > 32: the TMA/DMMA GEMM kernel over 3-D tensor maps
+          # Float32 with even M <= 32, P <= 16, N % 4 == 0: the warp-private FFMA2 kernel (8 or 16 lanes per product, idle row lanes,
+          # odd P, the largest product that still fits its shared-memory stages, and one that does not)
+          (2, 4, 1), (16, 64, 16), (30, 8, 3), (32, 128, 16), (32, 256, 16), (18, 12, 15)]
 
 
 def _to_np(t):
