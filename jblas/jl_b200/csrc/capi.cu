@@ -193,6 +193,18 @@ static int get_encode_tiled()
 static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esize, uint64_t rows, uint64_t cols,
                         uint64_t ld, uint32_t box_r, uint32_t box_c)
 {
+    // cuTensorMapEncodeTiled costs 1-2 us, as much as the launch itself on small problems: callers that multiply the same
+    // buffers again (every benchmark loop, every K panel of a pipeline) hit a small per-thread cache of encoded maps.
+    // A tensor map is a pure function of these eight values, so a stale entry cannot exist.
+    struct Entry { const void* base; uint64_t rows, cols, ld; uint32_t box_r, box_c; int dt, esize; bool valid; CUtensorMap map; };
+    static thread_local Entry cache[8] = {};
+    static thread_local unsigned next_slot = 0;
+    for (const Entry& e : cache)
+        if (e.valid && e.base == base && e.rows == rows && e.cols == cols && e.ld == ld && e.box_r == box_r && e.box_c == box_c &&
+            e.dt == (int)dt && e.esize == esize) {
+            *map = e.map;
+            return 0;
+        }
     if (int rc = get_encode_tiled()) return rc;
     cuuint64_t gdim[2] = {rows, cols};
     cuuint64_t gstride[1] = {ld * (uint64_t)esize};
@@ -202,6 +214,9 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType 
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(JBLAS_B200_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    Entry& slot = cache[next_slot++ % 8];
+    slot.base = base; slot.rows = rows; slot.cols = cols; slot.ld = ld; slot.box_r = box_r; slot.box_c = box_c;
+    slot.dt = (int)dt; slot.esize = esize; slot.map = *map; slot.valid = true;
     return 0;
 }
 
