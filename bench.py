@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the jmul! path on B200 (contract: see the task brief, section 4).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c4a|c4b|c5|fb] [--kernel auto|dmma|simt]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c4a|c4b|c5|fb|fb32] [--kernel auto|dmma|simt]
 
 One "step" = one product D = A*X over one batch of synthetic N(0,1) input (mrandn, src/randmat.jl:5-14).
   N = 1  : BASELINE.json configs[1]  -- Float64 M=N=K=8192 (the config the metric is quoted on).
@@ -210,11 +210,15 @@ def run_batched(args):
 
     jb.init(0)
     M, N, P, batch = FB_SHAPE
-    A = jb.mrandn_batch(batch, M, N, "float64", seed=SEED_A)
-    X = jb.mrandn_batch(batch, N, P, "float64", seed=SEED_X)
-    D = jb.empty_colmajor_batch(batch, M, P, "float64", fill=float("nan"))
+    f32 = args.workload == "fb32"  # same shape in Float32 (the reference is generic in T), twice the products
+    dtn, es = ("float32", 4) if f32 else ("float64", 8)
+    if f32:
+        batch *= 2
+    A = jb.mrandn_batch(batch, M, N, dtn, seed=SEED_A)
+    X = jb.mrandn_batch(batch, N, P, dtn, seed=SEED_X)
+    D = jb.empty_colmajor_batch(batch, M, P, dtn, fill=float("nan"))
     flops = 2.0 * M * N * P * batch
-    algo_bytes = (M * N + N * P + M * P) * 8 * batch  # every matrix read or written exactly once
+    algo_bytes = (M * N + N * P + M * P) * es * batch  # every matrix read or written exactly once
     for _ in range(max(args.warmup, 3)):
         jb.fastmul_batched_(D, A, X)
     torch.cuda.synchronize()
@@ -240,11 +244,11 @@ def run_batched(args):
     achieved = algo_bytes / (ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"fastmul_batched_dmma@{M}x{N}x{P}x{batch}")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{'fastmul_batched_f32_warp' if f32 else 'fastmul_batched_dmma'}@{M}x{N}x{P}x{batch}")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                "kernel": "fastmul_batched_dmma_kernel<2,2,8,1>", "kernel_ms": ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel": "fastmul_batched_f32_warp_kernel<8,14>" if f32 else "fastmul_batched_dmma_kernel<2,2,8,1,true>", "kernel_ms": ms, "algorithmic_bytes_per_launch": algo_bytes,
                 "flops_per_launch": flops, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src}; a copy bandwidth, 1 read : 1 write -- this "
                 "kernel reads 2.4 bytes per byte written, so a fraction slightly above 1 is possible)"}
     # e2e: the C-ABI host-pointer entry on pinned host batches (chunked H2D / kernel / D2H pipeline inside the call)
@@ -253,7 +257,7 @@ def run_batched(args):
     L = _lib.lib()
     Ah = np.ascontiguousarray(A.transpose(1, 2).cpu().numpy()).transpose(0, 2, 1)  # (batch, M, N), column-major matrices
     Xh = np.ascontiguousarray(X.transpose(1, 2).cpu().numpy()).transpose(0, 2, 1)
-    Dh = np.full((batch, P, M), np.nan).transpose(0, 2, 1)
+    Dh = np.full((batch, P, M), np.nan, dtype=Ah.dtype).transpose(0, 2, 1)
     bases = [a.base if a.base is not None else a for a in (Ah, Xh, Dh)]
     for a in bases:
         _lib.check(L.jblas_b200_host_register(a.ctypes.data, a.nbytes))
@@ -268,11 +272,11 @@ def run_batched(args):
         for a in bases:
             L.jblas_b200_host_unregister(a.ctypes.data)
     assert not np.isnan(Dh).any()
-    e2e = {"value": flops / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": (M * N + N * P) * 8 * batch, "d2h_bytes_per_step": M * P * 8 * batch,
+    e2e = {"value": flops / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": (M * N + N * P) * es * batch, "d2h_bytes_per_step": M * P * es * batch,
            "steps": steps, "ms_per_step": 1e3 * sec, "pcie_gbs": algo_bytes / sec / 1e9,
-           "api": "jblas_b200_fastmul_batched_f64 (host pointers, pinned by jblas_b200_host_register; PCIe-bound: 1.5 flop per byte moved)"}
+           "api": f"jblas_b200_fastmul_batched_{'f32' if f32 else 'f64'} (host pointers, pinned by jblas_b200_host_register; PCIe-bound: 1.5 flop per byte moved)"}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not f32:  # the fastmul! restatement is Float64 (the published number is)
         import oracle
 
         nb = 200_000  # bounded sample: 200k of the 10^6 products (1.9 GB of the workload), repeated until ~10 s have passed
@@ -295,9 +299,9 @@ def run_batched(args):
     value = flops / (ms * 1e-3) / 1e12
     published_tflops = 2.0 * M * N * P / (FB_PUBLISHED_NS * 1e-9) / 1e12
     line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / published_tflops, "dtype": "f64",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None if f32 else value / published_tflops, "dtype": "f32" if f32 else "f64",
             "data": "synthetic N(0,1), device-generated Philox (mrandn analogue)",
-            "config": {"workload": f"fastmul! batched: {batch} independent Float64 products D({M}x{P}) = A({M}x{N}) * X({N}x{P}) per launch (SURVEY 8f-1)",
+            "config": {"workload": f"fastmul! batched: {batch} independent {'Float32' if f32 else 'Float64'} products D({M}x{P}) = A({M}x{N}) * X({N}x{P}) per launch (SURVEY 8f-1)",
                        "products_per_s": batch / (ms * 1e-3), "ns_per_product": ms * 1e6 / batch,
                        "vs_baseline_note": f"BASELINE.md publishes {FB_PUBLISHED_NS} ns per product (1 CPU thread, author's machine) = {published_tflops:.4f} TFLOP/s",
                        "l2": f"inputs larger than L2: {algo_bytes / 2**20:.0f} MiB per step vs 126 MB L2"},
@@ -557,7 +561,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["fb"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["fb", "fb32"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "dmma", "simt", "tf32x3"])
     ap.add_argument("--panel-k", type=int, default=2048)
     ap.add_argument("--first-panel-k", type=int, default=256, help="shorter first K panel of the A broadcast (0 = same as the others)")
@@ -567,10 +571,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large workloads)")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.workload == "fb":
+        if args.workload in ("fb", "fb32"):
             raise SystemExit("--impl reference times the jmul! loop nest on the GEMM workloads; the fb leg reports its CPU figure in cpu_baseline")
         return run_reference(args)
-    if args.workload == "fb":
+    if args.workload in ("fb", "fb32"):
         return run_batched(args)
     return run_gpu(args)
 

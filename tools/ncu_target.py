@@ -14,10 +14,11 @@ from jblas.jl_b200 import api  # noqa: E402
 if sys.argv[1] == "batched":  # python tools/ncu_target.py batched M N P batch [reps]   (jBLAS names: D MxP = A MxN * X NxP)
     M, N, P, batch = (int(v) for v in sys.argv[2:6])
     reps = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+    bdt = sys.argv[7] if len(sys.argv) > 7 else "float64"
     jb.init(0)
-    A = jb.mrandn_batch(batch, M, N, "float64", seed=1)
-    X = jb.mrandn_batch(batch, N, P, "float64", seed=2)
-    D = jb.empty_colmajor_batch(batch, M, P, "float64")
+    A = jb.mrandn_batch(batch, M, N, bdt, seed=1)
+    X = jb.mrandn_batch(batch, N, P, bdt, seed=2)
+    D = jb.empty_colmajor_batch(batch, M, P, bdt)
     for _ in range(reps):
         jb.fastmul_batched_(D, A, X)
     torch.cuda.synchronize()
