@@ -138,3 +138,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+@pytest.mark.parametrize("fname,dtype,limit", [("r1_size_sweep_per_kernel.json", "float64", 0.05), ("r1_size_sweep_f32_per_kernel.json", "float32", 0.12)])
+def test_planner_pick_is_close_to_the_measured_best(jb, fname, dtype, limit):
+    """Regression guard for the planner's cost model (capi.cu: make_plan): on every shape of the committed per-kernel B200
+    sweeps (tools/size_sweep.py --all) the kernel it picks must be within `limit` of the fastest registered kernel.
+    (Without a GPU the occupancy of the one-CTA-per-tile kernels falls back to their launch bounds; the picks may then
+    differ from the on-device ones, the bound still has to hold.)"""
+    import json
+
+    path = os.path.join(ROOT, "profiles", fname)
+    sweep = json.load(open(path))
+    checked = 0
+    for key, row in sweep.items():
+        per = row.get("per_kernel_ms")
+        if not per or not key.startswith(dtype):
+            continue
+        M, N, K = (int(v) for v in key.split("_")[1].split("x"))
+        pick = jb.plan(M, K, N, dtype)["kernel"]
+        assert pick in per, (key, pick)
+        best = min(per.values())
+        assert per[pick] <= (1.0 + limit) * best, (key, pick, per[pick], best)
+        checked += 1
+    assert checked >= 10
