@@ -143,6 +143,8 @@ gemm_x_plus_c!(D::AbstractMatrix{T}, A::AbstractMatrix{T}, X::AbstractMatrix{T},
 `D[:,:,b] = A[:,:,b] * X[:,:,b]` for every `b` in ONE launch: the B200 form of `fastmul!` (src/kernels.jl:202-208) for a
 collection of small matrices (a dense `Array{T,3}` is exactly `batch` column-major matrices back to back).
 """
+function fastmul_batched! end
+
 for (T, sym) in ((Float64, :jblas_b200_fastmul_batched_f64), (Float32, :jblas_b200_fastmul_batched_f32))
     @eval function fastmul_batched!(D::Array{$T,3}, A::Array{$T,3}, X::Array{$T,3})
         M, P, B = size(D)
