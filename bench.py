@@ -311,6 +311,80 @@ def run_batched(args):
     return 0
 
 
+def parity_sample(D, A, X, n_rows=48, n_cols=24, seed=5, extra_rel=0.0):
+    """Checker, outside every timed region: a sampled sub-grid of this rank's D shard against the CPU oracle chain on the
+    identical input bits (each element's chain is independent -- jmul!'s tile loops, src/gemm.jl:313 -- so sampling is
+    legitimate).  The shard's first/last rows and columns (the seams between ranks) are always in the sample."""
+    import numpy as np
+    import torch
+
+    import oracle
+
+    M, ns = D.shape
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rows = np.unique(np.concatenate([[0, 1, M - 2, M - 1, 127, 128], rng.integers(0, M, n_rows)]).clip(0, M - 1))
+    cols = np.unique(np.concatenate([[0, 1, ns - 2, ns - 1], rng.integers(0, ns, n_cols)]).clip(0, ns - 1))
+    tr, tc = torch.from_numpy(rows).to(D.device), torch.from_numpy(cols).to(D.device)
+    As = np.asfortranarray(A[tr, :].cpu().numpy())
+    Xs = np.asfortranarray(X[:, tc].cpu().numpy())
+    got = np.asfortranarray(D[tr][:, tc].cpu().numpy())
+    want = oracle.oracle_gemm(As, Xs)
+    ok, worst = oracle.error_bound_ok(got, want, As, Xs, extra_rel=extra_rel)
+    return {"rows": int(rows.size), "cols": int(cols.size), "bit_identical": bool(got.tobytes() == want.tobytes()),
+            "within_bound": bool(ok), "worst_err_over_bound": float(worst), "nan_free": bool(not torch.isnan(D).any().item())}
+
+
+def merge_parity(dist, dev, world, mine):
+    """All ranks' samples -> one object (every rank must pass)."""
+    import torch
+
+    flags = torch.tensor([int(mine["bit_identical"]), int(mine["within_bound"]), int(mine["nan_free"]), -mine["worst_err_over_bound"]],
+                         device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    return {"rows": mine["rows"], "cols": mine["cols"], "ranks": world, "bit_identical": bool(flags[0].item() == 1),
+            "within_bound": bool(flags[1].item() == 1), "nan_free": bool(flags[2].item() == 1), "worst_err_over_bound": float(-flags[3].item()),
+            "checker": "oracle/oracle_gemm.c chain on the same input bits; per rank: rows x cols of its D shard incl. the shard seams"}
+
+
+def time_other_config(jb, name, kernel=None, extra_rel=0.0):
+    """One of the other BASELINE configs on one GPU: device-resident, CUDA events, buffers rotated so that consecutive
+    launches never find their operands in L2 (>= 300 MB of distinct A/X/D), sampled parity against the oracle."""
+    import torch
+
+    from jblas.jl_b200 import api
+
+    dtype, M, N, K, desc = WORKLOADS[name]
+    es = 8 if dtype == "float64" else 4
+    bytes_ = (M * K + K * N + M * N) * es
+    sets = max(1, min(8, -(-300_000_000 // bytes_))) if bytes_ < 300_000_000 else 1
+    bufs = [(jb.mrandn(M, K, dtype, seed=SEED_A + 2 * i), jb.mrandn(K, N, dtype, seed=SEED_X + 2 * i), jb.empty_colmajor(M, N, dtype, fill=float("nan")))
+            for i in range(sets)]
+    flops = 2.0 * M * N * K
+    reps = int(max(2, min(200, 0.4 / max(flops / 30e12, 1e-5))))
+    for A, X, D in bufs:
+        api._gemm(D, A, X, False, kernel)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        A, X, D = bufs[i % sets]
+        api._gemm(D, A, X, False, kernel)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    A, X, D = bufs[0]
+    par = parity_sample(D, A, X, extra_rel=extra_rel)
+    nominal = FP64_NOMINAL_TFLOPS if dtype == "float64" else FP32_NOMINAL_TFLOPS
+    out = {"config": name, "workload": desc, "kernel": jb.plan(M, K, N, dtype, kernel=kernel)["kernel"], "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12,
+           "frac_of_nominal": flops / (ms * 1e-3) / 1e12 / nominal, "nominal_peak": nominal, "algorithmic_gbs": bytes_ / (ms * 1e-3) / 1e9,
+           "reps": reps, "l2": f"{sets} rotating operand sets ({sets * bytes_ / 1e6:.0f} MB)" if sets > 1 else f"operands {bytes_ / 1e6:.0f} MB > L2",
+           "parity_check": par}
+    del bufs, A, X, D
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     # stdout must carry exactly ONE JSON line.  Libraries (NCCL's version banner, torchrun notices) printf() to fd 1,
     # so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved real stdout at the end.
@@ -324,6 +398,7 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_group = None
     if world != args.gpus:
         if world == 1 and args.gpus > 1:  # convenience: relaunch ourselves under torchrun (children get the real stdout)
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
@@ -340,6 +415,7 @@ def run_gpu(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
             os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # host-side waits (an NCCL barrier would spin a kernel on every GPU)
 
     from jblas.jl_b200 import build
 
@@ -414,6 +490,9 @@ def run_gpu(args):
     if rank == 0:
         sampler.stop()
     assert not torch.isnan(D).any().item(), "NaN sentinel survived: some element of D was not written"
+    # ---- parity of what was just timed (checker, outside the timed region): every rank samples its own D shard ----
+    parity = merge_parity(dist, dev, world, parity_sample(D, A, X, extra_rel=(2.0 ** -18 if args.kernel == "tf32x3" else 0.0)))
+    assert parity["within_bound"] and parity["nan_free"], f"parity check failed: {parity}"
 
     # ---- roofline of the dominant kernel (the GEMM kernel itself: at N=1 the step IS one launch) ----
     roofline = None
@@ -469,11 +548,23 @@ def run_gpu(args):
         }
 
     # ---- e2e: the reference-facing call with HOST buffers (H2D of A and X, D2H of D inside the timed region) ----
-    e2e = None if args.no_e2e else run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_step, selector)
+    e2e = None if args.no_e2e else run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_step, selector, cpu_group)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(dtype, M, N, K, target_s=12.0)
+
+    # ---- the other BASELINE configs, so that every config's speed AND parity is in the driver's own run ----
+    other = None
+    strong_c5 = None
+    if wl == "c2" and not args.no_other_configs:
+        del D, X, A
+        torch.cuda.empty_cache()
+        if world == 1:
+            other = [time_other_config(jb, "c4a"), time_other_config(jb, "c4b"), time_other_config(jb, "c3"),
+                     time_other_config(jb, "c3", kernel=jb.F32_3XTF32, extra_rel=2.0 ** -18)]
+            other[-1]["config"] = "c3_3xtf32"
+        strong_c5 = run_strong_c5(args, jb, dist, dev, world, rank, selector)
 
     if rank == 0:
         line = {
@@ -484,6 +575,9 @@ def run_gpu(args):
                        "parallelism": f"column-shard x{world}" + (f", A broadcast ({sg.bcast}) in {len(sg.panels)} K-panels (first {sg.panels[0][1] - sg.panels[0][0]}, then {args.panel_k})" if world > 1 else ""),
                        "l2": f"inputs larger than L2: A+X+D = {(M * K + K * sg.shard_cols + M * sg.shard_cols) * es / 2**20:.0f} MiB per GPU vs 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "parity_check": parity, "other_configs": other, "strong_c5": strong_c5,
+            "build": dict(build.build_info(), mode=build.LAST_BUILD_MODE,
+                          note="mode = what build.build() did in THIS process: 'reused' = the in-tree .so that travelled with the snapshot was newer than every source"),
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -493,7 +587,63 @@ def run_gpu(args):
     return 0
 
 
-def run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_step, selector):
+C5_ONE_GPU_FILE = os.path.join(ROOT, "profiles", "c5_1gpu.json")
+
+
+def run_strong_c5(args, jb, dist, dev, world, rank, selector):
+    """BASELINE configs[4]: Float64 32768^3, column-sharded over `world` GPUs (strong scaling), A (8 GiB) resident on rank 0
+    and delivered in K panels behind the multiplies.  1 warm-up + 3 timed steps, max over ranks, sampled parity per rank.
+    `efficiency` = T1 / (world * T_world) with T1 the one-GPU time of the same code: measured in this run when world == 1
+    (and written to gpurun_out/), otherwise the committed profiles/c5_1gpu.json."""
+    import torch
+
+    from jblas.jl_b200.multigpu import ShardedGemm
+
+    n = 32768
+    sg = ShardedGemm(n, n, n, panel_k=args.panel_k, kernel=selector, first_panel_k=args.first_panel_k or None, bcast=args.bcast)
+    A = jb.mrandn(n, n, "float64", seed=SEED_A) if rank == 0 else jb.empty_colmajor(n, n, "float64")
+    X = jb.mrandn(n, sg.shard_cols, "float64", seed=SEED_X, first_col=sg.c0)
+    D = jb.empty_colmajor(n, sg.shard_cols, "float64", fill=float("nan"))
+    sg(D, A, X)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    steps = 3 if world > 1 else 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sg(D, A, X)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    parity = merge_parity(dist, dev, world, parity_sample(D, A, X, n_rows=24, n_cols=12))
+    bcast = sg.bcast
+    sg.close()
+    del A, X, D, sg
+    torch.cuda.empty_cache()
+    flops = 2.0 * n * n * n
+    out = {"workload": WORKLOADS["c5"][4], "n_gpus": world, "steps": steps, "ms_per_step": ms, "tflops": flops / (ms * 1e-3) / 1e12,
+           "frac_of_nominal_per_gpu": flops / (ms * 1e-3) / 1e12 / world / FP64_NOMINAL_TFLOPS, "scaling": "strong", "transport": bcast,
+           "parity_check": parity}
+    if world == 1:
+        out["efficiency"] = 1.0
+        out["t1_ms"], out["t1_source"] = ms, "this run"
+    else:
+        try:
+            ref = json.load(open(C5_ONE_GPU_FILE))
+            out["t1_ms"], out["t1_source"] = float(ref["ms_per_step"]), "profiles/c5_1gpu.json: " + ref.get("source", "")
+            out["efficiency"] = out["t1_ms"] / (world * ms)
+        except Exception:
+            out["efficiency"] = None
+    return out
+
+
+def run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_step, selector, cpu_group=None):
     """Same metric through the public host-facing API: every step copies that step's inputs host->device from
     pinned host memory and reads the result back."""
     import numpy as np
@@ -524,35 +674,41 @@ def run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_st
         h2d, d2h = Ah.nbytes + Xh.nbytes, Dh.nbytes
         return {"value": flops_step * steps / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": steps, "ms_per_step": 1e3 * sec / steps, "api": "jblas_b200_gemm_f64 (host pointers, pinned by jblas_b200_host_register)"}
-    # N > 1: pinned host shards; root uploads A, every rank uploads its X block and downloads its D block
-    tdt = torch.float64 if dtype == "float64" else torch.float32
-    Xh = torch.empty((sg.shard_cols, K), dtype=tdt).pin_memory(); Xh.copy_(X.t())
-    Dh = torch.empty((sg.shard_cols, M), dtype=tdt).pin_memory()
-    Ah = None
-    if rank == 0:
-        Ah = torch.empty((K, M), dtype=tdt).pin_memory(); Ah.copy_(A.t())
-
-    def step():
-        # pipelined host-facing form: A panels H2D -> broadcast, X / D column blocks H2D / D2H overlapped with the GEMMs
-        sg.from_host(Dh, Ah, Xh, D, A, X)
-
-    step()
-    dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
+    # N > 1: the SINGLE-PROCESS multi-GPU entry of the C ABI, jblas_b200_mgpu_gemm_* -- what a Julia `jmul!(D, A, X; gpus = N)`
+    # hits: one host process, the whole A / X / D in pinned host memory, N GPUs driven from it.  Rank 0 makes the call on
+    # all N GPUs; the other ranks of this torchrun job hold no GPU work meanwhile and wait on a HOST-side (gloo) barrier.
+    n_total = sg.n_total
+    result = [None]
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    dist.barrier()
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    h2d = (M * K * es if rank == 0 else 0) + K * sg.shard_cols * es
-    tot = torch.tensor([float(h2d), float(M * sg.shard_cols * es)], device=dev, dtype=torch.float64)
-    dist.all_reduce(tot)
-    return {"value": flops_step * steps / (ms.item() * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tot[0].item()),
-            "d2h_bytes_per_step": int(tot[1].item()), "steps": steps, "ms_per_step": ms.item() / steps,
-            "api": "ShardedGemm.from_host on pinned host shards (H2D of A on rank 0 + X shard per rank, D2H of D shard per rank, pipelined)"}
+    dist.barrier(group=cpu_group)
+    if rank == 0:
+        ndt = np.float64 if dtype == "float64" else np.float32
+        Ah = np.asfortranarray(A.cpu().numpy())
+        Xh = np.empty((K, n_total), dtype=ndt, order="F")
+        chunk = 4096
+        for c0 in range(0, n_total, chunk):  # the one global X (the ranks' shards are column blocks of it), generated on this GPU
+            c1 = min(c0 + chunk, n_total)
+            Xh[:, c0:c1] = jb.mrandn(K, c1 - c0, dtype, seed=SEED_X, first_col=c0).cpu().numpy()
+        Dh = np.full((M, n_total), np.nan, dtype=ndt, order="F")
+        torch.cuda.empty_cache()
+        with jb.pinned(Ah, Xh, Dh):
+            jb.jmul_(Dh, Ah, Xh, kernel=selector, gpus=world)  # warm-up: per-GPU contexts, workspaces, peer access
+            t = time.perf_counter()
+            for _ in range(steps):
+                jb.jmul_(Dh, Ah, Xh, kernel=selector, gpus=world)
+            sec = time.perf_counter() - t
+        assert not np.isnan(Dh).any(), "NaN sentinel survived in the multi-GPU host result"
+        # parity of the end-to-end result: rank 0's own device-resident shard D (already checked against the oracle above) is
+        # the first column block of the same product
+        same = bool(np.array_equal(Dh[:, :sg.shard_cols], D.cpu().numpy()))
+        result[0] = {"value": flops_step * steps / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(Ah.nbytes + Xh.nbytes),
+                     "d2h_bytes_per_step": int(Dh.nbytes), "steps": steps, "ms_per_step": 1e3 * sec / steps,
+                     "first_shard_equals_device_resident_result": same,
+                     "api": f"jblas_b200_mgpu_gemm_{'f64' if dtype == 'float64' else 'f32'} (ONE host process, host pointers pinned by jblas_b200_host_register, "
+                            f"{world} GPUs: A slices over every GPU's own PCIe link + NVLink peer pulls, X / D column blocks per GPU; wall clock around the call)"}
+        del Ah, Xh, Dh
+    dist.barrier(group=cpu_group)
+    return result[0]
 
 
 def main():
@@ -569,6 +725,7 @@ def main():
                     help="N > 1: how A reaches the other GPUs (multigpu.py); auto = copy-engine pulls over CUDA IPC if every rank can map A, else NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (very large workloads)")
+    ap.add_argument("--no-other-configs", action="store_true", help="default workload only: skip the other BASELINE configs (c3, c4a, c4b at N=1; 32768^3 strong at every N)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.workload in ("fb", "fb32"):

@@ -58,7 +58,8 @@ extern "C" {
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
 /* Bind the calling process to CUDA device `device` (one process per GPU) and create the context
- * (streams, events, staging buffers).  Idempotent for the same device. */
+ * (streams, events, staging buffers).  Idempotent for the same device.  Every entry makes the bound device current
+ * on the calling thread; device pointers must live on it (JBLAS_B200_EINVAL otherwise). */
 int jblas_b200_init(int device);
 int jblas_b200_shutdown(void);
 int jblas_b200_version(void);
@@ -74,6 +75,21 @@ int jblas_b200_gemm_f64(double* D, const double* A, const double* X, int64_t M, 
                         int64_t lda, int64_t ldx, int accumulate, int kernel);
 int jblas_b200_gemm_f32(float* D, const float* A, const float* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
                         int64_t lda, int64_t ldx, int accumulate, int mode);
+
+/* ---- the same call on SEVERAL GPUs of this process (single-node multi-GPU mode) --------
+ * Replaces: jmul!(D, A, X)  src/gemm.jl:244-246 with its outer column-tile loop (src/gemm.jl:313) cut across GPUs:
+ * GPU g of `ngpus` (devices 0..ngpus-1) owns one contiguous column block of X and D and needs all of A.  Host pointers,
+ * synchronous, same arguments as jblas_b200_gemm_*.  Every K panel of A crosses PCIe once, one slice per GPU over that
+ * GPU's own link, and reaches the other GPUs over NVLink (copy engines, peer access); X blocks go up and D blocks come
+ * back over each GPU's link while the panels are multiplied.  Per element the k order is that of a single launch, so
+ * the result equals the one-GPU result bit for bit.  jblas_b200_mgpu_init(ngpus) creates the per-GPU contexts and
+ * enables peer access (ngpus <= 0: every visible GPU; returns the count); the gemm entries call it on demand.
+ * jblas_b200_time_last_ms() reports the wall-clock time of the call. */
+int jblas_b200_mgpu_init(int ngpus);
+int jblas_b200_mgpu_gemm_f64(double* D, const double* A, const double* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
+                             int64_t lda, int64_t ldx, int accumulate, int kernel, int ngpus);
+int jblas_b200_mgpu_gemm_f32(float* D, const float* A, const float* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
+                             int64_t lda, int64_t ldx, int accumulate, int mode, int ngpus);
 
 /* jBLAS-named forms on dense MMatrix-style storage (leading dimension = row count).
  * jmul!   src/gemm.jl:244      D(MxP) = A(MxN) * X(NxP)
@@ -192,6 +208,7 @@ float jblas_b200_time_last_ms(void);
 /* ---- pipe-rate probes (roofline denominators; registers only, no memory traffic) --------------------
  * kind: 0 = DFMA, 1 = DMMA m8n8k4, 2 = FFMA (independent chains, operands reused);
  *       3 = DMMA, 4 = DFMA, 5 = FFMA, 6 = FFMA2 in the GEMM micro-kernel operand pattern (8x8 outer product).
+ *       (Development builds with -DJBLAS_B200_TUNING_PROBES add shared-memory ablation kinds 7+; not shipped.)
  * Returns achieved TFLOP/s (2 flop per FMA) in *tflops. */
 int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms);
 

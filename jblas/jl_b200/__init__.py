@@ -2,7 +2,8 @@
 
 Layout:  csrc/   hand-written CUDA kernels + the C ABI (include/jblas_b200.h -> libjblas_b200.so)
          api.py  host-side mirror of the reference interface (jmul_, gemm_, fastmul_, kernel_, initkernel_, mrandn)
-         multigpu.py  column-block sharding of X/D across ranks + K-panel broadcast of A (torch.distributed / NCCL)
+         multigpu.py  column-block sharding of X/D across ranks + K-panel broadcast of A (torch.distributed / NCCL);
+                      the single-process form of the same mode is jmul_(..., gpus=n) -> jblas_b200_mgpu_gemm_*
 The CUDA library is the product: importing this package never falls back to a CPU implementation.
 """
 from .api import (  # noqa: F401
@@ -28,6 +29,8 @@ from .api import (  # noqa: F401
     kernel_,
     kernel_names,
     launch_count,
+    mgpu_init,
+    pinned,
     mrandn,
     plan,
     probe_pipe,

@@ -28,6 +28,9 @@ PROTOTYPES = {
     "jblas_b200_device_count": (c_int, []),
     "jblas_b200_gemm_f64": (c_int, _GEMM),
     "jblas_b200_gemm_f32": (c_int, _GEMM),
+    "jblas_b200_mgpu_init": (c_int, [c_int]),
+    "jblas_b200_mgpu_gemm_f64": (c_int, _GEMM + [c_int]),
+    "jblas_b200_mgpu_gemm_f32": (c_int, _GEMM + [c_int]),
     "jblas_b200_jmul_f64": (c_int, _JMUL),
     "jblas_b200_jmul_f32": (c_int, _JMUL),
     "jblas_b200_fastmul_f64": (c_int, _JMUL),

@@ -99,7 +99,45 @@ def _describe(x, name: str):
     return x.ctypes.data, r, c, ld, (DT_F64 if x.dtype == np.float64 else DT_F32), False
 
 
-def _gemm(D, A, X, accumulate: bool, selector: int | None):
+def mgpu_init(ngpus: int = 0) -> int:
+    """Create the per-GPU contexts of the single-process multi-GPU mode on devices 0..ngpus-1 and enable peer access
+    (ngpus <= 0: every visible GPU).  Returns the number of GPUs.  `jmul_(..., gpus=n)` calls it on demand."""
+    global _initialised_device
+    n = check(_lib.lib().jblas_b200_mgpu_init(int(ngpus)))
+    if _initialised_device is None:
+        _initialised_device = 0  # the library bound the process to device 0
+    return n
+
+
+class pinned:
+    """Context manager: page-lock caller-owned numpy arrays for the duration of a block (jblas_b200_host_register), so the
+    host-pointer entries DMA at full PCIe rate.  A Julia caller does the same once per buffer (julia/jBLASB200.jl: pin!)."""
+
+    def __init__(self, *arrays):
+        self.arrays = [a.base if (a.base is not None and isinstance(a.base, np.ndarray)) else a for a in arrays]
+        self.done = []
+
+    def __enter__(self):
+        init()
+        L = _lib.lib()
+        try:
+            for a in self.arrays:
+                check(L.jblas_b200_host_register(a.ctypes.data, a.nbytes))
+                self.done.append(a)
+        except Exception:
+            self.__exit__(None, None, None)
+            raise
+        return self
+
+    def __exit__(self, *exc):
+        L = _lib.lib()
+        for a in self.done:
+            L.jblas_b200_host_unregister(a.ctypes.data)
+        self.done = []
+        return False
+
+
+def _gemm(D, A, X, accumulate: bool, selector: int | None, gpus: int | None = None):
     pD, M, N, ldd, tD, devD = _describe(D, "D")
     pA, M2, K, lda, tA, devA = _describe(A, "A")
     pX, K2, N2, ldx, tX, devX = _describe(X, "X")
@@ -111,13 +149,24 @@ def _gemm(D, A, X, accumulate: bool, selector: int | None):
         raise ValueError("D, A and X must all be host arrays or all be GPU tensors")
     if not devD and not D.flags.writeable:
         raise ValueError("D must be writeable")
-    init()
     L = _lib.lib()
     if selector is None:
         selector = F64_AUTO if tD == DT_F64 else F32_EXACT
+    if gpus is not None and gpus != 1:
+        # single-process multi-GPU mode: host matrices only (device-resident shards are the torch.distributed mode, multigpu.py)
+        if devD:
+            raise ValueError("gpus=N takes host (numpy) matrices; for GPU-resident shards use multigpu.ShardedGemm")
+        mgpu_init(gpus)
+        fn = L.jblas_b200_mgpu_gemm_f64 if tD == DT_F64 else L.jblas_b200_mgpu_gemm_f32
+        check(fn(pD, pA, pX, M, K, N, ldd, lda, max(ldx, 1), int(accumulate), int(selector), int(gpus)))
+        return D
+    dev = init()
     if devD:
         import torch
 
+        for name, t in (("D", D), ("A", A), ("X", X)):
+            if t.device.index != dev:
+                raise ValueError(f"{name} lives on cuda:{t.device.index} but this process is bound to cuda:{dev} (one process per GPU)")
         stream = torch.cuda.current_stream(D.device).cuda_stream
         fn = L.jblas_b200_gemm_f64_dev if tD == DT_F64 else L.jblas_b200_gemm_f32_dev
         check(fn(pD, pA, pX, M, K, N, ldd, lda, max(ldx, 1), int(accumulate), int(selector), stream))
@@ -127,14 +176,16 @@ def _gemm(D, A, X, accumulate: bool, selector: int | None):
     return D
 
 
-def jmul_(D, A, X, Aprefetch=7, Xprefetch=7, A_loc=3, X_loc=3, D_loc=3, *, kernel: int | None = None):
+def jmul_(D, A, X, Aprefetch=7, Xprefetch=7, A_loc=3, X_loc=3, D_loc=3, *, kernel: int | None = None, gpus: int | None = None):
     """D = A*X into the preallocated column-major D; returns D.  (jmul!, src/gemm.jl:244-348)
 
     The five prefetch arguments of the reference (`Val{Aprefetch_freq}` ..., src/gemm.jl:245) are accepted and
     ignored: software prefetch is replaced by the asynchronous shared-memory pipeline.  Unlike the reference,
-    remainder rows/columns are computed.  `kernel` selects F64_AUTO/F64_DMMA/F64_SIMT (or F32_EXACT/F32_3XTF32)."""
+    remainder rows/columns are computed.  `kernel` selects F64_AUTO/F64_DMMA/F64_SIMT (or F32_EXACT/F32_3XTF32).
+    `gpus=n` (host matrices) runs the single-node multi-GPU mode: column blocks of X and D per GPU -- jmul!'s outer
+    column-tile loop, src/gemm.jl:313 -- through jblas_b200_mgpu_gemm_*; the result equals the one-GPU result bit for bit."""
     del Aprefetch, Xprefetch, A_loc, X_loc, D_loc
-    return _gemm(D, A, X, False, kernel)
+    return _gemm(D, A, X, False, kernel, gpus)
 
 
 gemm_ = jmul_  # BASELINE.json calls the same entry `gemm!`

@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(256) probe_ffma2_tile_kernel(float* out, int i
     if (s == 0x123456789abcdefull) out[0] = 1.f;
 }
 
+#ifdef JBLAS_B200_TUNING_PROBES  // development aid (tools/probe_ffma2.py): `python -m jblas.jl_b200.build --probes`; not in the shipped library
 // The exact-FP32 kernel's inner loop (gemm_simt_f32x2.cuh) on a resident shared-memory tile, without any global traffic:
 // what the FFMA2 stream sustains WITH its shared-memory operand loads.  MODE bits: 1 = __syncthreads per 32-deep k-tile,
 // 2 = A through four LDS.64 instead of two LDS.128, 4 = no X loads (registers reused), 8 = no A loads.
@@ -268,5 +269,7 @@ __global__ void __launch_bounds__(256, MINB) probe_ffma2_lds_kernel(float* out, 
         for (int p = 0; p < 4; ++p) s ^= acc[j][p];
     if (s == 0x123456789abcdefull) out[0] = 1.f;
 }
+
+#endif  // JBLAS_B200_TUNING_PROBES
 
 }  // namespace jb

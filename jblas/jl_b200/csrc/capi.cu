@@ -7,6 +7,7 @@
 #include "../../../include/jblas_b200.h"
 
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -47,33 +48,96 @@ static int fail(int code, const char* fmt, ...)
     } while (0)
 
 // ---------------------------------------------------------------------------------------------------------
-// context (one per process: one process per GPU)
+// contexts.  jblas_b200_init binds the process to ONE GPU (one process per GPU: the torch.distributed mode); the
+// single-process multi-GPU entries (jblas_b200_mgpu_*) create a context on every GPU they drive.  Every host routine
+// below works on cur(): the context the calling thread is currently issuing to.
 // ---------------------------------------------------------------------------------------------------------
+static constexpr int kMaxDevices = 16;
+// Work counters of the persistent TMA kernels: {next tile, CTAs done} pairs, all zero at rest (a kernel leaves its pair
+// zeroed, gemm_dmma_tma.cuh).  Two LIVE kernels must never share a pair.  Kernels on one stream never overlap, so a pair
+// belongs to a STREAM: the first kStreamSlots pairs are handed out per stream handle (cudaStreamPerThread: per thread);
+// launches captured into a CUDA graph may replay anywhere later, so those take pairs from a separate ring instead
+// (replays of ONE graph must not overlap each other).  When the stream table is full the launch falls back to the
+// static tile stride (ctr == nullptr), which needs no counter.
+static constexpr int kStreamSlots = 4096, kCaptureSlots = 4096, kTileCtrSlots = kStreamSlots + kCaptureSlots;
 struct Context {
     int device = -1;
     int num_sms = 0;
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t copy_stream = nullptr;  // H2D for the host-pointer entry points
     cudaStream_t d2h_stream = nullptr;   // D2H (its own stream: PCIe is full duplex, one stream would serialise the two)
+    cudaStream_t peer_stream = nullptr;  // multi-GPU: copy-engine pulls of A panels from the other GPUs over NVLink
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
     void* ws[3] = {nullptr, nullptr, nullptr};  // device staging for D, A, X (host-pointer entry points)
     size_t ws_bytes[3] = {0, 0, 0};
     float last_ms = 0.f;
     bool attrs_set = false;
-    int* tile_ctr = nullptr;  // kTileCtrSlots x {next tile, CTAs done}: work counters of the persistent TMA kernels, all zero at rest
+    int* tile_ctr = nullptr;  // kTileCtrSlots pairs
+    std::mutex slot_mu;
+    std::map<cudaStream_t, int> slot_of;
+    uint32_t capture_seq = 0;
+    // rates of this box, measured once (calibrate()): they size the panel ramp of the host-pointer pipeline
+    double h2d_bytes_per_s = 0, dmma_flops_per_s = 0, ffma2_flops_per_s = 0;
 };
-// Each launch takes the next slot of the ring; a kernel leaves its slot zeroed (gemm_dmma_tma.cuh).  A slot could only be
-// shared by two live kernels if kTileCtrSlots launches were in flight at once, far beyond what the driver queues.
-static constexpr int kTileCtrSlots = 8192;
-static std::atomic<uint32_t> g_tile_ctr_seq{0};
-static Context g_ctx;
-static std::mutex g_mu;  // calls are serialised per context (SURVEY 8b "Threading")
+static Context g_ctxs[kMaxDevices];
+static int g_primary = -1;                     // device bound by jblas_b200_init
+static int g_mgpu = 0;                         // GPUs 0..g_mgpu-1 carry a context and peer access (jblas_b200_mgpu_init)
+static thread_local Context* t_cur = nullptr;  // set while a multi-GPU routine issues work to another device
+static Context& cur() { return t_cur ? *t_cur : g_ctxs[g_primary < 0 ? 0 : g_primary]; }
+#define g_ctx (cur())
+static std::mutex g_mu;  // host-pointer calls are serialised (SURVEY 8b "Threading")
 static std::atomic<int64_t> g_launches{0};
 
 static int require_init()
 {
-    if (g_ctx.device < 0) return fail(JBLAS_B200_ENOTINIT, "jblas_b200_init has not been called (no CPU fallback exists)");
+    if (g_primary < 0 && !t_cur) return fail(JBLAS_B200_ENOTINIT, "jblas_b200_init has not been called (no CPU fallback exists)");
+    // entries may be called from any host thread, and a fresh thread's current device is 0, not the bound one
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess || d != cur().device) CUDA_TRY(cudaSetDevice(cur().device));
     return 0;
+}
+// The operands of a device entry must live on the bound GPU: a pointer from another device would be dereferenced by
+// kernels launched here with this context's counters and streams (illegal address instead of a clean error).
+static int check_on_device(const void* p, const char* what)
+{
+    if (!p) return 0;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;  // unknown to the runtime (e.g. a mapping the driver API made): not ours to reject
+    }
+    if (a.type == cudaMemoryTypeDevice && a.device != cur().device)
+        return fail(JBLAS_B200_EINVAL, "%s lives on device %d but the library is bound to device %d", what, a.device, cur().device);
+    return 0;
+}
+
+static int* tile_counter_for(cudaStream_t s)
+{
+    Context& c = cur();
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) {
+        cudaGetLastError();  // legacy default stream while another stream captures: not capturing itself
+        cap = cudaStreamCaptureStatusNone;
+    }
+    std::lock_guard<std::mutex> lk(c.slot_mu);
+    if (cap == cudaStreamCaptureStatusActive) return c.tile_ctr + 2 * (kStreamSlots + (int)(c.capture_seq++ % kCaptureSlots));
+    if (s == cudaStreamPerThread) {
+        static thread_local int per_thread_slot[kMaxDevices];  // 0 = none yet, else slot + 1
+        int& mine = per_thread_slot[c.device];
+        if (!mine) {
+            if ((int)c.slot_of.size() >= kStreamSlots) return nullptr;
+            const int slot = (int)c.slot_of.size();
+            c.slot_of[(cudaStream_t)(uintptr_t)(0x100000000ull + slot)] = slot;  // reserves the slot (key is no real handle)
+            mine = slot + 1;
+        }
+        return c.tile_ctr + 2 * (mine - 1);
+    }
+    auto it = c.slot_of.find(s);
+    if (it == c.slot_of.end()) {
+        if ((int)c.slot_of.size() >= kStreamSlots) return nullptr;
+        it = c.slot_of.emplace(s, (int)c.slot_of.size()).first;
+    }
+    return c.tile_ctr + 2 * it->second;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -261,7 +325,7 @@ static int launch_dmma_tma(void* D, const void* A, const void* X, int M, int N, 
         const char* e = getenv("JBLAS_B200_STATIC_TILES");
         static_tiles = (e && atoi(e)) ? 1 : 0;
     }
-    int* ctr = static_tiles ? nullptr : g_ctx.tile_ctr + 2 * (g_tile_ctr_seq.fetch_add(1, std::memory_order_relaxed) % kTileCtrSlots);
+    int* ctr = static_tiles ? nullptr : tile_counter_for(s);
     gemm_dmma_tma_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mapA, mapX, (double*)D, M, N, K, ldd, tiles_m, tiles_n,
                                                                            group_m, pa, px, ctr, (const double*)Cin, ldc);
     return 0;
@@ -630,6 +694,7 @@ static int gemm_dev_ex(int dtype, T* D, const T* A, const T* X, int64_t M, int64
     if (int rc = require_init()) return rc;
     if (int rc = validate(D, A, X, M, K, N, ldd, lda, ldx)) return rc;
     if (M == 0 || N == 0) return 0;
+    if (int rc = check_on_device(D, "D")) return rc;
     if (Cin && ldc < M) return fail(JBLAS_B200_EINVAL, "ldc=%lld < M=%lld", (long long)ldc, (long long)M);
     if (Xadd && K > 0 && ldxa < K) return fail(JBLAS_B200_EINVAL, "ld of the matrix added to X = %lld < K=%lld", (long long)ldxa, (long long)K);
     const int accumulate = Cin != nullptr;
@@ -650,8 +715,17 @@ static int gemm_dev_ex(int dtype, T* D, const T* A, const T* X, int64_t M, int64
     // need.  For products big enough to matter, the misaligned operand is first copied into a stream-ordered scratch
     // buffer with an even leading dimension (HBM-speed pass, a few % of the GEMM), then the fast path runs.
     const int vec = 16 / (int)sizeof(T);
-    T* tmpA = nullptr;
-    T* tmpX = nullptr;
+    struct Scratch {  // stream-ordered scratch, returned to the pool on EVERY exit path
+        cudaStream_t s;
+        void* p[2] = {nullptr, nullptr};
+        ~Scratch()
+        {
+            for (void* q : p)
+                if (q) cudaFreeAsync(q, s);
+        }
+    } scratch{s};
+    T*& tmpA = reinterpret_cast<T*&>(scratch.p[0]);
+    T*& tmpX = reinterpret_cast<T*&>(scratch.p[1]);
     if (Xadd) {
         const int64_t ld2 = (K + vec - 1) / vec * vec;
         CUDA_TRY(cudaMallocAsync((void**)&tmpX, (size_t)ld2 * N * sizeof(T), s));
@@ -661,7 +735,11 @@ static int gemm_dev_ex(int dtype, T* D, const T* A, const T* X, int64_t M, int64
         X = tmpX;
         ldx = ld2;
     }
-    if (2.0 * (double)M * (double)N * (double)K >= 1.0e9) {
+    // the 3xTF32 path re-splits both operands into its own K-major scratch anyway: re-aligning first would be a wasted HBM pass
+    const bool splits_itself = dtype == JBLAS_B200_DT_F32 && (selector == JBLAS_B200_F32_3XTF32 ||
+                                                               (selector >= JBLAS_B200_EXPLICIT_BASE && selector - JBLAS_B200_EXPLICIT_BASE < NUM_KERNELS &&
+                                                                g_kernels[selector - JBLAS_B200_EXPLICIT_BASE].family == FAM_TF32X3));
+    if (!splits_itself && 2.0 * (double)M * (double)N * (double)K >= 1.0e9) {
         RealignJob jobs[2];
         int njobs = 0;
         if (!is_aligned16(A) || lda % vec) {
@@ -671,7 +749,7 @@ static int gemm_dev_ex(int dtype, T* D, const T* A, const T* X, int64_t M, int64
             A = tmpA;
             lda = ld2;
         }
-        if (!is_aligned16(X) || ldx % vec) {
+        if (!tmpX && (!is_aligned16(X) || ldx % vec)) {  // (the X + C scratch above is born aligned)
             const int64_t ld2 = (K + vec - 1) / vec * vec;
             CUDA_TRY(cudaMallocAsync((void**)&tmpX, (size_t)ld2 * N * sizeof(T), s));
             jobs[njobs++] = make_realign_job<T>(X, ldx, tmpX, ld2, K, N);
@@ -685,16 +763,12 @@ static int gemm_dev_ex(int dtype, T* D, const T* A, const T* X, int64_t M, int64
         }
     }
     Plan p;
-    int rc = make_plan(dtype, M, K, N, lda, ldx, A, X, selector, &p);
-    if (!rc) rc = set_all_attrs();
-    if (!rc) {
-        const KernelInfo& k = g_kernels[p.kidx];
-        rc = k.launch[p.aligned ? 1 : 0][accumulate ? 1 : 0](D, A, X, (int)M, (int)N, (int)K, ldd, lda, ldx, p.tiles_m, p.tiles_n,
-                                                             p.group_m, s, Cin, ldc);
-    }
-    if (tmpA) cudaFreeAsync(tmpA, s);
-    if (tmpX) cudaFreeAsync(tmpX, s);
-    if (rc) return rc;
+    if (int rc = make_plan(dtype, M, K, N, lda, ldx, A, X, selector, &p)) return rc;
+    if (int rc = set_all_attrs()) return rc;
+    const KernelInfo& k = g_kernels[p.kidx];
+    if (int rc = k.launch[p.aligned ? 1 : 0][accumulate ? 1 : 0](D, A, X, (int)M, (int)N, (int)K, ldd, lda, ldx, p.tiles_m, p.tiles_n,
+                                                                  p.group_m, s, Cin, ldc))
+        return rc;
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -725,154 +799,378 @@ static int ensure_ws(int i, size_t bytes)
     return 0;
 }
 
-// Optional timeline of the host-pointer pipeline (JBLAS_B200_TRACE=1): one CUDA event per stage, printed to stderr.
+// Optional timeline of the host-pointer pipeline (JBLAS_B200_TRACE=1): one CUDA event per stage, printed to stderr
+// (times are relative to the start of the call on the SAME GPU: events of different devices cannot be subtracted).
 struct HostTrace {
     bool on = false;
-    std::vector<cudaEvent_t> ev;
-    std::vector<std::string> tag;
-    void mark(const char* what, int64_t idx, cudaStream_t st)
+    struct Mark { int g; cudaEvent_t ev; std::string tag; };
+    std::vector<Mark> marks;
+    void mark(int g, const char* what, int64_t idx, cudaStream_t st)
     {
         if (!on) return;
         cudaEvent_t e;
         cudaEventCreate(&e);
         cudaEventRecord(e, st);
-        ev.push_back(e);
-        tag.push_back(std::string(what) + " " + std::to_string(idx));
+        marks.push_back({g, e, std::string(what) + " " + std::to_string(idx)});
     }
-    void dump(cudaEvent_t t0)
+    void dump(int G, Context** ctx)
     {
         if (!on) return;
-        for (size_t i = 0; i < ev.size(); ++i) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, t0, ev[i]);
-            fprintf(stderr, "[jblas_b200 trace] %8.3f ms  %s\n", ms, tag[i].c_str());
-            cudaEventDestroy(ev[i]);
-        }
+        for (int g = 0; g < G; ++g)
+            for (const Mark& m : marks) {
+                if (m.g != g) continue;
+                float ms = 0;
+                cudaSetDevice(ctx[g]->device);
+                cudaEventElapsedTime(&ms, ctx[g]->ev0, m.ev);
+                fprintf(stderr, "[jblas_b200 trace] gpu %d %8.3f ms  %s\n", ctx[g]->device, ms, m.tag.c_str());
+                cudaEventDestroy(m.ev);
+            }
+        marks.clear();
     }
 };
 
-// Synchronous host-pointer GEMM: the literal drop-in for jmul!(D, A, X).  PCIe (H2D ~55 GB/s, D2H ~52 GB/s, full duplex)
-// and the tensor pipe are overlapped with a two-phase schedule over the (K panel, column block) grid:
-//   phase 1 -- K-PANEL major over the FIRST half of the columns: for each panel p the copy stream uploads A[:, kp] and the
-//              matching rows of X for those columns, the compute stream does  D[:, :N1] (+)= A[:, kp] * X[kp, :N1]
-//              (accumulate = p > 0: ascending k per element, i.e. the chain -- and for every kernel here every bit -- of
-//              a single launch; kernel! semantics, src/kernels.jl:226).  H2D-bound, but the pipe already works.
+// Rates of THIS box that size the panel ramp below, measured once per context (a slower PCIe slot or a power-capped GPU
+// must not get a ramp tuned on another machine): pinned H2D bandwidth (32 MiB copy) and the register-only DMMA / FFMA2
+// warp-tile probes.  JBLAS_B200_H2D_GBS / JBLAS_B200_F64_TFLOPS / JBLAS_B200_F32_TFLOPS override the measurement.
+static int calibrate()
+{
+    Context& c = cur();
+    if (c.h2d_bytes_per_s > 0) return 0;
+    auto env = [](const char* name) -> double { const char* e = getenv(name); return e ? atof(e) : 0.0; };
+    double h2d = env("JBLAS_B200_H2D_GBS") * 1e9, f64 = env("JBLAS_B200_F64_TFLOPS") * 1e12, f32 = env("JBLAS_B200_F32_TFLOPS") * 1e12;
+    cudaStream_t st = c.stream;
+    float ms = 0.f;
+    if (h2d <= 0) {
+        const size_t bytes = (size_t)32 << 20;
+        void *h = nullptr, *d = nullptr;
+        CUDA_TRY(cudaMallocHost(&h, bytes));
+        if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaFreeHost(h); cudaGetLastError(); return fail(JBLAS_B200_ENOMEM, "calibration buffer"); }
+        memset(h, 0, bytes);
+        for (int rep = 0; rep < 3; ++rep) {  // the last repetition counts
+            cudaEventRecord(c.ev0, st);
+            cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
+            cudaEventRecord(c.ev1, st);
+            cudaStreamSynchronize(st);
+            cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+        }
+        cudaFree(d);
+        cudaFreeHost(h);
+        CUDA_TRY(cudaGetLastError());
+        h2d = ms > 0 ? (double)bytes / (ms * 1e-3) : 50e9;
+    }
+    void* out = nullptr;
+    if (f64 <= 0 || f32 <= 0) CUDA_TRY(cudaMalloc(&out, 256));
+    if (f64 <= 0) {
+        const int iters = 1500;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(c.ev0, st);
+            probe_dmma_tile_kernel<<<c.num_sms, 256, 0, st>>>((double*)out, iters, 1.0000001, 1e-9);
+            cudaEventRecord(c.ev1, st);
+            cudaStreamSynchronize(st);
+            cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+        }
+        g_launches += 4;
+        f64 = ms > 0 ? 2.0 * 256 * 32 * iters * (double)c.num_sms * 8 / (ms * 1e-3) : 36e12;
+    }
+    if (f32 <= 0) {
+        const int iters = 4000;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(c.ev0, st);
+            probe_ffma2_tile_kernel<<<c.num_sms * 2, 256, 0, st>>>((float*)out, iters, 1.0000001f, 1e-9f);
+            cudaEventRecord(c.ev1, st);
+            cudaStreamSynchronize(st);
+            cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+        }
+        g_launches += 4;
+        f32 = ms > 0 ? 2.0 * 64 * iters * (double)c.num_sms * 2 * 256 / (ms * 1e-3) : 60e12;
+    }
+    if (out) cudaFree(out);
+    CUDA_TRY(cudaGetLastError());
+    c.h2d_bytes_per_s = h2d;
+    c.dmma_flops_per_s = f64;
+    c.ffma2_flops_per_s = f32;
+    if (getenv("JBLAS_B200_TRACE"))
+        fprintf(stderr, "[jblas_b200 trace] calibration on device %d: H2D %.1f GB/s, DMMA tile %.2f TFLOP/s, FFMA2 tile %.2f TFLOP/s\n", c.device,
+                h2d / 1e9, f64 / 1e12, f32 / 1e12);
+    return 0;
+}
+
+// Event pool of the host pipeline (timing disabled; reused across calls)
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    size_t next = 0;
+    int get(cudaEvent_t* out)
+    {
+        if (next == ev.size()) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev.push_back(e);
+        }
+        *out = ev[next++];
+        return 0;
+    }
+};
+static EventPool g_pool[kMaxDevices];
+
+// [c0, c1) of the N columns owned by shard g of G; remainder columns go to the LAST shards (multigpu.column_shard).
+static void column_shard(int64_t N, int G, int g, int64_t* c0, int64_t* c1)
+{
+    const int64_t base = N / G, rem = N % G;
+    auto count = [&](int r) { return base + (r >= G - rem ? 1 : 0); };
+    int64_t at = 0;
+    for (int r = 0; r < g; ++r) at += count(r);
+    *c0 = at;
+    *c1 = at + count(g);
+}
+
+// Synchronous host-pointer GEMM: the literal drop-in for jmul!(D, A, X), on `G` GPUs of this process (G = 1: the bound one).
+//
+// Partition: GPU g owns a column block of X and D -- the outer `cc` loop of jmul! (src/gemm.jl:313) -- and needs
+// all of A.  PCIe (one link per GPU, full duplex), NVLink and the tensor pipes are overlapped with a two-phase schedule over
+// the (K panel, column block) grid of every GPU:
+//   phase 1 -- K-PANEL major over the FIRST half of the GPU's columns.  Panel p of A is cut into G column slices; GPU u
+//              uploads slice u over ITS OWN PCIe link (so A crosses the host links once, in parallel), every other GPU pulls
+//              that slice from u's memory with its copy engines over NVLink (no kernel, no SM); with the panel complete the
+//              compute stream does  D[:, :N1] (+)= A[:, kp] * X[kp, :N1]  (accumulate = p > 0: ascending k per element,
+//              i.e. the chain -- and for every kernel here every bit -- of a single launch; kernel! semantics,
+//              src/kernels.jl:226).  The matching rows of X travel with the panel.
 //   phase 2 -- A is now resident: the remaining columns go COLUMN-BLOCK major, one full-K launch per block, while the
 //              finished blocks (first the whole phase-1 half) travel back on a separate D2H stream.
-// Only the last block's D2H is exposed.  Small problems degenerate to one panel / one block.
+// Only the last block's D2H is exposed.  Small problems degenerate to one panel / one block.  One host thread issues
+// everything (all calls are asynchronous); an event is always recorded before any other stream is told to wait on it.
+template <typename T>
+static int gemm_host_issue(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
+                           int64_t ldx, int accumulate, int selector, int G, Context** ctx, const int64_t* shard_c0, const int64_t* shard_ns,
+                           HostTrace& trace)
+{
+    const size_t es = sizeof(T);
+    const int vec = 16 / (int)es;
+    // device copies are dense with even leading dimensions so the 16-byte / TMA staging paths apply
+    const int64_t dM = (M + vec - 1) / vec * vec, dK = (K + vec - 1) / vec * vec;
+    struct Dev {
+        int64_t c0 = 0, ns = 0, N1 = 0;
+        T *dD = nullptr, *dA = nullptr, *dX = nullptr;
+    } dv[kMaxDevices];
+    auto on = [&](int g) -> int {  // make GPU g the one this thread issues to
+        t_cur = ctx[g];
+        CUDA_TRY(cudaSetDevice(ctx[g]->device));
+        return 0;
+    };
+    int64_t ns_max = 0;
+    (void)N;
+    for (int g = 0; g < G; ++g) {  // every shard here is non-empty (the caller dropped GPUs without columns)
+        dv[g].c0 = shard_c0[g];
+        dv[g].ns = shard_ns[g];
+        if (dv[g].ns > ns_max) ns_max = dv[g].ns;
+        if (int rc = on(g)) return rc;
+        g_pool[ctx[g]->device].next = 0;
+        if (int rc = ensure_ws(0, (size_t)dM * dv[g].ns * es)) return rc;
+        if (K > 0) {
+            if (int rc = ensure_ws(1, (size_t)dM * K * es)) return rc;
+            if (int rc = ensure_ws(2, (size_t)dK * dv[g].ns * es)) return rc;
+        }
+        dv[g].dD = (T*)ctx[g]->ws[0];
+        dv[g].dA = (T*)ctx[g]->ws[1];
+        dv[g].dX = (T*)ctx[g]->ws[2];
+        CUDA_TRY(cudaEventRecord(ctx[g]->ev0, ctx[g]->copy_stream));
+        if (accumulate)
+            CUDA_TRY(cudaMemcpy2DAsync(dv[g].dD, dM * es, D + dv[g].c0 * ldd, ldd * es, M * es, dv[g].ns, cudaMemcpyHostToDevice, ctx[g]->copy_stream));
+    }
+    auto d2h = [&](int g, int64_t n0, int64_t nc) -> int {  // compute stream -> D2H stream hand-over for local columns [n0, n0+nc)
+        Context& c = *ctx[g];
+        CUDA_TRY(cudaEventRecord(c.ev_copy, c.stream));
+        CUDA_TRY(cudaStreamWaitEvent(c.d2h_stream, c.ev_copy, 0));
+        CUDA_TRY(cudaMemcpy2DAsync(D + (dv[g].c0 + n0) * ldd, ldd * es, dv[g].dD + n0 * dM, dM * es, M * es, nc, cudaMemcpyDeviceToHost, c.d2h_stream));
+        trace.mark(g, "d2h done, n0 =", n0, c.d2h_stream);
+        return 0;
+    };
+    if (K == 0) {
+        for (int g = 0; g < G; ++g) {
+            if (int rc = on(g)) return rc;
+            Context& c = *ctx[g];
+            CUDA_TRY(cudaEventRecord(c.ev_copy, c.copy_stream));
+            CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+            if (int rc = gemm_dev<T>(dtype, dv[g].dD, dv[g].dA, dv[g].dX, M, 0, dv[g].ns, dM, dM, 1, accumulate, selector, c.stream)) return rc;
+            if (int rc = d2h(g, 0, dv[g].ns)) return rc;
+        }
+        return 0;
+    }
+    // ---- schedule (shared by all GPUs: the K panels are a collective object) ----
+    const size_t panel_bytes = (size_t)64 << 20;
+    const bool big = (size_t)(M + ns_max) * K * es > 2 * panel_bytes;
+    // K panels of ~64 MiB of A (at least 512 columns: a shorter accumulate pass re-reads its D tiles too often); the first
+    // one is a quarter panel so the multiply starts early
+    int64_t kp = K;
+    if (big) {
+        kp = (int64_t)(panel_bytes / ((size_t)M * es));
+        kp = kp / 64 * 64;
+        if (kp < 512) kp = 512;
+        if (kp > K) kp = K;
+    }
+    const int64_t kfirst = (kp < K && kp >= 1024) ? kp / 4 : (kp < K && kp >= 512 ? 256 : kp);
+    // phase-1 columns: everything for small problems, otherwise the first half (multiple of 128)
+    for (int g = 0; g < G; ++g) {
+        dv[g].N1 = dv[g].ns;
+        if (big && (size_t)M * dv[g].ns * es > panel_bytes && dv[g].ns >= 512) dv[g].N1 = ((dv[g].ns / 2) + 127) / 128 * 128;
+    }
+    // phase-2 column blocks: ~64 MiB of D each
+    int64_t nb = (int64_t)(panel_bytes / ((size_t)M * es));
+    nb = nb / 128 * 128;
+    if (nb < 128) nb = 128;
+    // Panel ramp.  Panel i+1 is uploaded while panel i is multiplied, so without a bubble it can exceed panel i only by the
+    // ratio of the two rates in contraction columns per second: a GPU's link moves (M/G + N1) elements per column, the
+    // multiply spends 2*M*N1 flops on it.  8192^3 f64 on one GPU: 573 vs 515 columns per ms -> x1.11 per step (a fixed
+    // 256 -> 1024 jump left the tensor pipe idle for 1.3 ms at the start, JBLAS_B200_TRACE timeline).
+    double growth = 0.0;
+    if (big && kfirst < kp) {
+        if (int rc = on(0)) return rc;
+        if (int rc = calibrate()) return rc;
+        const Context& c = *ctx[0];
+        // sustained rates of the ACCUMULATE passes relative to the register-only probes (a pass re-reads its D tiles):
+        // 34.5 of 36.8 TFLOP/s in f64, 52 of 61 exact f32; 3xTF32 runs at ~6.2x the DMMA rate
+        const double flops_per_s = dtype == JBLAS_B200_DT_F64 ? 0.9375 * c.dmma_flops_per_s
+                                                              : (selector == JBLAS_B200_F32_3XTF32 ? 6.2 * c.dmma_flops_per_s : 0.85 * c.ffma2_flops_per_s);
+        const int64_t n1 = dv[0].N1 > 0 ? dv[0].N1 : 1;
+        growth = (c.h2d_bytes_per_s / (((double)M / G + (double)n1) * es)) / (flops_per_s / (2.0 * (double)M * (double)n1));
+        if (growth > 2.0) growth = 2.0;
+        if (growth < 1.02) growth = 0.0;  // copy-bound: nothing to gain, keep the two-size scheme
+    }
+    // ---- phase 1 ----
+    double ramp = (double)kfirst;
+    int panel = 0;
+    std::vector<cudaEvent_t> a_up(G), x_up(G);
+    for (int64_t k0 = 0; k0 < K; ++panel) {
+        int64_t kstep = (k0 == 0) ? kfirst : kp;
+        if (growth > 0.0 && k0 > 0) {
+            ramp *= growth;
+            kstep = ((int64_t)(ramp / 64.0 + 0.5)) * 64;
+            if (kstep < kfirst) kstep = kfirst;
+            if (kstep > kp) kstep = kp;
+        }
+        const int64_t kc = (K - k0 < kstep) ? (K - k0) : kstep;
+        const int acc = (accumulate || k0 > 0) ? 1 : 0;
+        // slice u of the panel: columns [k0 + kc*u/G, k0 + kc*(u+1)/G), rounded to 16 columns
+        auto slice = [&](int u) -> int64_t { return u >= G ? k0 + kc : k0 + (kc * u / G) / 16 * 16; };
+        for (int u = 0; u < G; ++u) {  // uploads, each GPU over its own link
+            if (int rc = on(u)) return rc;
+            Context& c = *ctx[u];
+            const int64_t ka = slice(u), kb = slice(u + 1);
+            if (kb > ka)
+                CUDA_TRY(cudaMemcpy2DAsync(dv[u].dA + ka * dM, dM * es, A + ka * lda, lda * es, M * es, kb - ka, cudaMemcpyHostToDevice, c.copy_stream));
+            if (G > 1) {
+                if (int rc = g_pool[c.device].get(&a_up[u])) return rc;
+                CUDA_TRY(cudaEventRecord(a_up[u], c.copy_stream));
+            }
+            CUDA_TRY(cudaMemcpy2DAsync(dv[u].dX + k0, dK * es, X + dv[u].c0 * ldx + k0, ldx * es, kc * es, dv[u].N1, cudaMemcpyHostToDevice, c.copy_stream));
+            trace.mark(u, "h2d A slice + X rows (phase-1 columns) done, k0 =", k0, c.copy_stream);
+            if (int rc = g_pool[c.device].get(&x_up[u])) return rc;
+            CUDA_TRY(cudaEventRecord(x_up[u], c.copy_stream));
+        }
+        for (int g = 0; g < G; ++g) {  // pulls over NVLink, then the panel product
+            if (int rc = on(g)) return rc;
+            Context& c = *ctx[g];
+            if (G > 1) {
+                for (int i = 1; i < G; ++i) {
+                    const int u = (g + i) % G;  // every GPU starts with a different peer: no slice owner serves G-1 pulls at once
+                    const int64_t ka = slice(u), kb = slice(u + 1);
+                    if (kb == ka) continue;
+                    CUDA_TRY(cudaStreamWaitEvent(c.peer_stream, a_up[u], 0));
+                    CUDA_TRY(cudaMemcpyPeerAsync(dv[g].dA + ka * dM, c.device, dv[u].dA + ka * dM, ctx[u]->device, (size_t)(kb - ka) * dM * es, c.peer_stream));
+                }
+                cudaEvent_t have;
+                if (int rc = g_pool[c.device].get(&have)) return rc;
+                CUDA_TRY(cudaEventRecord(have, c.peer_stream));
+                trace.mark(g, "A panel complete (peer slices pulled), k0 =", k0, c.peer_stream);
+                CUDA_TRY(cudaStreamWaitEvent(c.stream, have, 0));
+            }
+            CUDA_TRY(cudaStreamWaitEvent(c.stream, x_up[g], 0));
+            if (int rc = gemm_dev<T>(dtype, dv[g].dD, dv[g].dA + k0 * dM, dv[g].dX + k0, M, kc, dv[g].N1, dM, dM, dK, acc, selector, c.stream)) return rc;
+            trace.mark(g, "gemm phase-1 panel done, k0 =", k0, c.stream);
+        }
+        k0 += kc;
+    }
+    // ---- phase 2 ----
+    const int64_t tail = 256;  // the last block's D2H is the one transfer nothing hides: split a short tail block off the final one
+    for (int g = 0; g < G; ++g) {
+        if (int rc = on(g)) return rc;
+        Context& c = *ctx[g];
+        if (int rc = d2h(g, 0, dv[g].N1)) return rc;
+        for (int64_t n0 = dv[g].N1, nc = 0; n0 < dv[g].ns; n0 += nc) {
+            const int64_t left = dv[g].ns - n0;
+            nc = left < nb ? left : nb;
+            if (big && left <= nb && left >= 3 * tail) nc = left - tail;
+            CUDA_TRY(cudaMemcpy2DAsync(dv[g].dX + n0 * dK, dK * es, X + (dv[g].c0 + n0) * ldx, ldx * es, K * es, nc, cudaMemcpyHostToDevice, c.copy_stream));
+            trace.mark(g, "h2d X column block done, n0 =", n0, c.copy_stream);
+            CUDA_TRY(cudaEventRecord(c.ev_copy, c.copy_stream));
+            CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
+            if (int rc = gemm_dev<T>(dtype, dv[g].dD + n0 * dM, dv[g].dA, dv[g].dX + n0 * dK, M, K, nc, dM, dM, dK, accumulate ? 1 : 0, selector, c.stream))
+                return rc;
+            trace.mark(g, "gemm phase-2 block done, n0 =", n0, c.stream);
+            if (int rc = d2h(g, n0, nc)) return rc;
+        }
+    }
+    return 0;
+}
+
+template <typename T>
+static int gemm_host_multi(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
+                           int64_t ldx, int accumulate, int selector, int G, Context** ctx)
+{
+    if (int rc = validate(D, A, X, M, K, N, ldd, lda, ldx)) return rc;
+    if (M == 0 || N == 0) return 0;
+    Context* const saved = t_cur;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    HostTrace trace;
+    trace.on = getenv("JBLAS_B200_TRACE") != nullptr;
+    // column shards (multigpu.column_shard: remainder columns go to the last GPUs); GPUs left without a column sit the call out
+    Context* act[kMaxDevices];
+    int64_t c0s[kMaxDevices], nss[kMaxDevices];
+    const int G_all = G;
+    G = 0;
+    for (int g = 0; g < G_all; ++g) {
+        int64_t c0, c1;
+        column_shard(N, G_all, g, &c0, &c1);
+        if (c1 == c0) continue;
+        act[G] = ctx[g];
+        c0s[G] = c0;
+        nss[G] = c1 - c0;
+        ++G;
+    }
+    ctx = act;
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = gemm_host_issue<T>(dtype, D, A, X, M, K, N, ldd, lda, ldx, accumulate, selector, G, ctx, c0s, nss, trace);
+    // Success or not, nothing may stay in flight: the copies reference the caller's host buffers and the shared workspaces.
+    cudaError_t first = cudaSuccess;
+    for (int g = 0; g < G; ++g) {
+        cudaSetDevice(ctx[g]->device);
+        if (!rc) cudaEventRecord(ctx[g]->ev1, ctx[g]->d2h_stream);
+        for (cudaStream_t st : {ctx[g]->d2h_stream, ctx[g]->copy_stream, ctx[g]->peer_stream, ctx[g]->stream}) {
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess && first == cudaSuccess) first = e;
+        }
+    }
+    const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (!rc && first != cudaSuccess) rc = fail(JBLAS_B200_ECUDA, "host-pointer pipeline: %s", cudaGetErrorString(first));
+    float ms = 0.f;
+    Context& report = g_ctxs[g_primary >= 0 ? g_primary : 0];
+    if (!rc && G == 1 && cudaEventElapsedTime(&ms, ctx[0]->ev0, ctx[0]->ev1) == cudaSuccess) report.last_ms = ms;  // device time of the pipeline
+    else report.last_ms = rc ? 0.f : (float)wall_ms;  // several GPUs: events of different devices cannot be subtracted
+    cudaGetLastError();
+    if (!rc) trace.dump(G, ctx);
+    t_cur = saved;
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return rc;
+}
+
 template <typename T>
 static int gemm_host(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda,
                      int64_t ldx, int accumulate, int selector)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (int rc = require_init()) return rc;
-    if (int rc = validate(D, A, X, M, K, N, ldd, lda, ldx)) return rc;
-    if (M == 0 || N == 0) return 0;
-    const size_t es = sizeof(T);
-    // device copies are dense with even leading dimensions so the 16-byte / TMA staging paths apply
-    const int vec = 16 / (int)es;
-    const int64_t dM = (M + vec - 1) / vec * vec, dK = (K + vec - 1) / vec * vec;
-    if (int rc = ensure_ws(0, (size_t)dM * N * es)) return rc;
-    if (K > 0) {
-        if (int rc = ensure_ws(1, (size_t)dM * K * es)) return rc;
-        if (int rc = ensure_ws(2, (size_t)dK * N * es)) return rc;
-    }
-    T* dD = (T*)g_ctx.ws[0];
-    T* dA = (T*)g_ctx.ws[1];
-    T* dX = (T*)g_ctx.ws[2];
-    cudaStream_t cs = g_ctx.copy_stream, ks = g_ctx.stream, os = g_ctx.d2h_stream;
-    HostTrace trace;
-    trace.on = getenv("JBLAS_B200_TRACE") != nullptr;
-    CUDA_TRY(cudaEventRecord(g_ctx.ev0, cs));
-    if (accumulate) CUDA_TRY(cudaMemcpy2DAsync(dD, dM * es, D, ldd * es, M * es, N, cudaMemcpyHostToDevice, cs));
-    auto d2h = [&](int64_t n0, int64_t nc) -> int {  // compute stream -> D2H stream hand-over for columns [n0, n0+nc)
-        CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, ks));
-        CUDA_TRY(cudaStreamWaitEvent(os, g_ctx.ev_copy, 0));
-        CUDA_TRY(cudaMemcpy2DAsync(D + n0 * ldd, ldd * es, dD + n0 * dM, dM * es, M * es, nc, cudaMemcpyDeviceToHost, os));
-        trace.mark("d2h done, n0 =", n0, os);
-        return 0;
-    };
-    if (K == 0) {
-        CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
-        CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
-        if (int rc = gemm_dev<T>(dtype, dD, dA, dX, M, 0, N, dM, dM, 1, accumulate, selector, ks)) return rc;
-        if (int rc = d2h(0, N)) return rc;
-    } else {
-        const size_t panel_bytes = (size_t)64 << 20;
-        const bool big = (size_t)(M + N) * K * es > 2 * panel_bytes;
-        // K panels of ~64 MiB of A; the first one is a quarter panel so the multiply starts early
-        int64_t kp = K;
-        if (big) {
-            kp = (int64_t)(panel_bytes / ((size_t)M * es));
-            kp = kp / 64 * 64;
-            if (kp < 256) kp = 256;
-            if (kp > K) kp = K;
-        }
-        const int64_t kfirst = (kp < K && kp >= 1024) ? kp / 4 : kp;
-        // phase-1 columns: everything for small problems, otherwise the first half (multiple of 128)
-        int64_t N1 = N;
-        if (big && (size_t)M * N * es > panel_bytes && N >= 512) N1 = ((N / 2) + 127) / 128 * 128;
-        // phase-2 column blocks: ~64 MiB of D each
-        int64_t nb = (int64_t)(panel_bytes / ((size_t)M * es));
-        nb = nb / 128 * 128;
-        if (nb < 128) nb = 128;
-        // Panel ramp.  Panel i+1 is uploaded while panel i is multiplied, so without a bubble it can exceed panel i only by the
-        // ratio of the two rates in contraction columns per second: H2D moves (M + N1) elements per column, the multiply
-        // spends 2*M*N1 flops on it.  8192^3 f64: 573 vs 515 columns per ms -> x1.11 per step (a fixed 256 -> 1024 jump left the
-        // tensor pipe idle for 1.3 ms at the start, JBLAS_B200_TRACE timeline).
-        double growth = 0.0;
-        if (big && kfirst < kp) {
-            const double h2d_bytes_per_s = 55e9;  // measured, pinned host memory
-            // sustained rates of the ACCUMULATE passes (a pass re-reads its D tiles): 34.5 of the 36 TFLOP/s in f64
-            const double flops_per_s = dtype == JBLAS_B200_DT_F64 ? 34.5e12 : (selector == JBLAS_B200_F32_3XTF32 ? 230e12 : 52e12);
-            growth = (h2d_bytes_per_s / ((double)(M + N1) * es)) / (flops_per_s / (2.0 * (double)M * (double)N1));
-            if (growth > 2.0) growth = 2.0;
-            if (growth < 1.02) growth = 0.0;  // copy-bound: nothing to gain, keep the two-size scheme
-        }
-        double ramp = (double)kfirst;
-        for (int64_t k0 = 0; k0 < K;) {
-            int64_t kstep = (k0 == 0) ? kfirst : kp;
-            if (growth > 0.0 && k0 > 0) {
-                ramp *= growth;
-                kstep = ((int64_t)(ramp / 64.0 + 0.5)) * 64;
-                if (kstep < kfirst) kstep = kfirst;
-                if (kstep > kp) kstep = kp;
-            }
-            const int64_t kc = (K - k0 < kstep) ? (K - k0) : kstep;
-            const int acc = (accumulate || k0 > 0) ? 1 : 0;
-            CUDA_TRY(cudaMemcpy2DAsync(dA + k0 * dM, dM * es, A + k0 * lda, lda * es, M * es, kc, cudaMemcpyHostToDevice, cs));
-            CUDA_TRY(cudaMemcpy2DAsync(dX + k0, dK * es, X + k0, ldx * es, kc * es, N1, cudaMemcpyHostToDevice, cs));
-            trace.mark("h2d A panel + X rows (phase-1 columns) done, k0 =", k0, cs);
-            CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
-            CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
-            if (int rc = gemm_dev<T>(dtype, dD, dA + k0 * dM, dX + k0, M, kc, N1, dM, dM, dK, acc, selector, ks)) return rc;
-            trace.mark("gemm phase-1 panel done, k0 =", k0, ks);
-            k0 += kc;
-        }
-        if (int rc = d2h(0, N1)) return rc;
-        // the last block's D2H is the one transfer nothing hides: split a short tail block off the final one
-        const int64_t tail = 256;
-        for (int64_t n0 = N1, nc = 0; n0 < N; n0 += nc) {
-            const int64_t left = N - n0;
-            nc = left < nb ? left : nb;
-            if (big && left <= nb && left >= 3 * tail) nc = left - tail;
-            CUDA_TRY(cudaMemcpy2DAsync(dX + n0 * dK, dK * es, X + n0 * ldx, ldx * es, K * es, nc, cudaMemcpyHostToDevice, cs));
-            trace.mark("h2d X column block done, n0 =", n0, cs);
-            CUDA_TRY(cudaEventRecord(g_ctx.ev_copy, cs));
-            CUDA_TRY(cudaStreamWaitEvent(ks, g_ctx.ev_copy, 0));
-            if (int rc = gemm_dev<T>(dtype, dD + n0 * dM, dA, dX + n0 * dK, M, K, nc, dM, dM, dK, accumulate ? 1 : 0, selector, ks))
-                return rc;
-            trace.mark("gemm phase-2 block done, n0 =", n0, ks);
-            if (int rc = d2h(n0, nc)) return rc;
-        }
-    }
-    CUDA_TRY(cudaEventRecord(g_ctx.ev1, os));
-    CUDA_TRY(cudaStreamSynchronize(os));
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    CUDA_TRY(cudaStreamSynchronize(ks));
-    cudaEventElapsedTime(&g_ctx.last_ms, g_ctx.ev0, g_ctx.ev1);
-    trace.dump(g_ctx.ev0);
-    return 0;
+    Context* one[1] = {&cur()};
+    return gemm_host_multi<T>(dtype, D, A, X, M, K, N, ldd, lda, ldx, accumulate, selector, 1, one);
 }
 
 // Host-pointer form of the fused products: plain staging (everything up, one product, D down) on the compute stream.
@@ -933,6 +1231,86 @@ static int fused_host(int dtype, T* D, const T* A, const T* X, const T* C, int64
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// context lifetime
+// ---------------------------------------------------------------------------------------------------------
+static int create_context(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(JBLAS_B200_ECUDA, "no CUDA device available (%s); jblas_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n || device >= kMaxDevices) return fail(JBLAS_B200_EINVAL, "device %d out of range [0,%d)", device, n < kMaxDevices ? n : kMaxDevices);
+    Context& c = g_ctxs[device];
+    if (c.device == device) return 0;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(JBLAS_B200_EUNSUPPORTED, "device %d is sm_%d%d; this library contains sm_100a code only", device,
+                    prop.major, prop.minor);
+    c.num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.d2h_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.peer_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c.ev0));
+    CUDA_TRY(cudaEventCreate(&c.ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc((void**)&c.tile_ctr, (size_t)kTileCtrSlots * 2 * sizeof(int)));
+    CUDA_TRY(cudaMemset(c.tile_ctr, 0, (size_t)kTileCtrSlots * 2 * sizeof(int)));
+    CUDA_TRY(cudaDeviceSynchronize());  // zero before any launch on the (non-blocking) library or caller streams
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;  // re-align scratch (cudaMallocAsync) stays cached across synchronisations
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
+    c.device = device;
+    c.attrs_set = false;
+    Context* saved = t_cur;
+    t_cur = &c;
+    int rc = set_all_attrs();
+    t_cur = saved;
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return rc;
+}
+
+static void destroy_context(Context& c)
+{
+    if (c.device < 0) return;
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 3; ++i) {
+        if (c.ws[i]) cudaFree(c.ws[i]);
+        c.ws[i] = nullptr;
+        c.ws_bytes[i] = 0;
+    }
+    if (c.tile_ctr) cudaFree(c.tile_ctr);
+    if (c.ev0) cudaEventDestroy(c.ev0);
+    if (c.ev1) cudaEventDestroy(c.ev1);
+    if (c.ev_copy) cudaEventDestroy(c.ev_copy);
+    for (cudaStream_t st : {c.stream, c.copy_stream, c.d2h_stream, c.peer_stream})
+        if (st) cudaStreamDestroy(st);
+    c.tile_ctr = nullptr;
+    c.ev0 = c.ev1 = c.ev_copy = nullptr;
+    c.stream = c.copy_stream = c.d2h_stream = c.peer_stream = nullptr;
+    c.slot_of.clear();
+    c.capture_seq = 0;
+    c.num_sms = 0;
+    c.attrs_set = false;
+    c.last_ms = 0.f;
+    c.h2d_bytes_per_s = c.dmma_flops_per_s = c.ffma2_flops_per_s = 0;
+    c.device = -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // exported C ABI
 // ---------------------------------------------------------------------------------------------------------
 extern "C" {
@@ -954,64 +1332,27 @@ int jblas_b200_device_count(void)
 int jblas_b200_init(int device)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_ctx.device == device) return 0;
-    if (g_ctx.device >= 0) return fail(JBLAS_B200_EINVAL, "already initialised on device %d (one process per GPU)", g_ctx.device);
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        cudaGetLastError();
-        return fail(JBLAS_B200_ECUDA, "no CUDA device available (%s); jblas_b200 has no CPU fallback",
-                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    }
-    if (device < 0 || device >= n) return fail(JBLAS_B200_EINVAL, "device %d out of range [0,%d)", device, n);
+    if (g_primary == device) return 0;
+    if (g_primary >= 0) return fail(JBLAS_B200_EINVAL, "already initialised on device %d (one process per GPU; the multi-GPU entries drive the others)", g_primary);
+    if (int rc = create_context(device)) return rc;
+    g_primary = device;
     CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(JBLAS_B200_EUNSUPPORTED, "device %d is sm_%d%d; this library contains sm_100a code only", device,
-                    prop.major, prop.minor);
-    g_ctx.num_sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.d2h_stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&g_ctx.ev0));
-    CUDA_TRY(cudaEventCreate(&g_ctx.ev1));
-    CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.ev_copy, cudaEventDisableTiming));
-    CUDA_TRY(cudaMalloc((void**)&g_ctx.tile_ctr, (size_t)kTileCtrSlots * 2 * sizeof(int)));
-    CUDA_TRY(cudaMemset(g_ctx.tile_ctr, 0, (size_t)kTileCtrSlots * 2 * sizeof(int)));
-    CUDA_TRY(cudaDeviceSynchronize());  // zero before any launch on the (non-blocking) library or caller streams
-    {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = ~0ull;  // re-align scratch (cudaMallocAsync) stays cached across synchronisations
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-    }
-    g_ctx.device = device;
-    g_ctx.attrs_set = false;
-    return set_all_attrs();
+    return 0;
 }
 
 int jblas_b200_shutdown(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_ctx.device < 0) return 0;
-    cudaSetDevice(g_ctx.device);
-    cudaDeviceSynchronize();
-    for (int i = 0; i < 3; ++i) {
-        if (g_ctx.ws[i]) cudaFree(g_ctx.ws[i]);
-        g_ctx.ws[i] = nullptr;
-        g_ctx.ws_bytes[i] = 0;
+    for (int d = 0; d < kMaxDevices; ++d) {
+        if (g_ctxs[d].device >= 0) cudaSetDevice(d);
+        for (cudaEvent_t e : g_pool[d].ev) cudaEventDestroy(e);
+        g_pool[d].ev.clear();
+        g_pool[d].next = 0;
+        destroy_context(g_ctxs[d]);
     }
-    if (g_ctx.tile_ctr) cudaFree(g_ctx.tile_ctr);
-    if (g_ctx.ev0) cudaEventDestroy(g_ctx.ev0);
-    if (g_ctx.ev1) cudaEventDestroy(g_ctx.ev1);
-    if (g_ctx.ev_copy) cudaEventDestroy(g_ctx.ev_copy);
-    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
-    if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
-    if (g_ctx.d2h_stream) cudaStreamDestroy(g_ctx.d2h_stream);
-    g_ctx = Context();
+    if (g_primary >= 0) cudaSetDevice(g_primary);
+    g_primary = -1;
+    g_mgpu = 0;
     return 0;
 }
 
@@ -1062,6 +1403,72 @@ int jblas_b200_gemm_f32(float* D, const float* A, const float* X, int64_t M, int
                         int64_t lda, int64_t ldx, int accumulate, int mode)
 {
     return gemm_host<float>(JBLAS_B200_DT_F32, D, A, X, M, K, N, ldd, lda, ldx, accumulate, mode);
+}
+
+// ---- single-process multi-GPU mode: the same host-pointer contract on `ngpus` GPUs ----
+
+int jblas_b200_mgpu_init(int ngpus)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(JBLAS_B200_ECUDA, "no CUDA device available (%s); jblas_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (ngpus <= 0) ngpus = n < kMaxDevices ? n : kMaxDevices;
+    if (ngpus > n || ngpus > kMaxDevices) return fail(JBLAS_B200_EINVAL, "%d GPUs requested, %d visible (at most %d supported)", ngpus, n, kMaxDevices);
+    if (g_primary >= ngpus) return fail(JBLAS_B200_EINVAL, "the process is bound to device %d, outside the requested set 0..%d", g_primary, ngpus - 1);
+    if (ngpus <= g_mgpu) return ngpus;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < ngpus; ++d)
+        if (int rc = create_context(d)) return rc;
+    for (int d = 0; d < ngpus; ++d) {
+        CUDA_TRY(cudaSetDevice(d));
+        for (int q = 0; q < ngpus; ++q) {
+            if (q == d) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, d, q);
+            if (!can) continue;  // cudaMemcpyPeerAsync still works (staged through the host), only slower
+            cudaError_t pe = cudaDeviceEnablePeerAccess(q, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(JBLAS_B200_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", d, q, cudaGetErrorString(pe));
+            cudaGetLastError();
+        }
+    }
+    if (g_primary < 0) g_primary = 0;
+    cudaSetDevice(prev >= 0 ? prev : g_primary);
+    g_mgpu = ngpus;
+    return ngpus;
+}
+
+}  // extern "C" (templates cannot have C linkage)
+template <typename T>
+static int mgpu_gemm(int dtype, T* D, const T* A, const T* X, int64_t M, int64_t K, int64_t N, int64_t ldd, int64_t lda, int64_t ldx,
+                     int accumulate, int selector, int ngpus)
+{
+    if (ngpus <= 0) return fail(JBLAS_B200_EINVAL, "ngpus must be positive");
+    if (ngpus > g_mgpu) {
+        int rc = jblas_b200_mgpu_init(ngpus);
+        if (rc < 0) return rc;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    Context* ctx[kMaxDevices];
+    for (int g = 0; g < ngpus; ++g) ctx[g] = &g_ctxs[g];
+    return gemm_host_multi<T>(dtype, D, A, X, M, K, N, ldd, lda, ldx, accumulate, selector, ngpus, ctx);
+}
+extern "C" {
+int jblas_b200_mgpu_gemm_f64(double* D, const double* A, const double* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
+                             int64_t lda, int64_t ldx, int accumulate, int kernel, int ngpus)
+{
+    return mgpu_gemm<double>(JBLAS_B200_DT_F64, D, A, X, M, K, N, ldd, lda, ldx, accumulate, kernel, ngpus);
+}
+int jblas_b200_mgpu_gemm_f32(float* D, const float* A, const float* X, int64_t M, int64_t K, int64_t N, int64_t ldd,
+                             int64_t lda, int64_t ldx, int accumulate, int mode, int ngpus)
+{
+    return mgpu_gemm<float>(JBLAS_B200_DT_F32, D, A, X, M, K, N, ldd, lda, ldx, accumulate, mode, ngpus);
 }
 
 // jBLAS naming: D is MxP, A is MxN, X is NxP (src/gemm.jl:244); dense MMatrix storage.
@@ -1119,10 +1526,10 @@ template <typename Cfg>
 static int launch_dmma_tma_batched(double* D, const double* A, const double* X, int M, int K, int N, int64_t batch, int64_t strideD,
                                    int64_t strideA, int64_t strideX, cudaStream_t s)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[kMaxDevices] = {};  // function attributes are per device
+    if (!attr_done[g_ctx.device]) {
         CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_done = true;
+        attr_done[g_ctx.device] = true;
     }
     CUtensorMap mapA, mapX;
     if (int rc = make_tmap_3d(&mapA, A, (uint64_t)M, (uint64_t)K, (uint64_t)batch, (uint64_t)M, (uint64_t)strideA, 16, 16)) return rc;
@@ -1132,7 +1539,7 @@ static int launch_dmma_tma_batched(double* D, const double* A, const double* X, 
     if (tiles > 0x7fffffffLL) return fail(JBLAS_B200_EINVAL, "batch too large: %lld tiles", (long long)tiles);
     int64_t grid = (int64_t)g_ctx.num_sms * Cfg::MIN_BLOCKS;
     if (grid > tiles) grid = tiles;
-    int* ctr = g_ctx.tile_ctr + 2 * (g_tile_ctr_seq.fetch_add(1, std::memory_order_relaxed) % kTileCtrSlots);
+    int* ctr = tile_counter_for(s);
     gemm_dmma_tma_kernel<Cfg, false, true><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, s>>>(
         mapA, mapX, D, M, N, K, (int64_t)M, tiles_m, tiles_n, tiles_m, kL2EvictNormal, kL2EvictNormal, ctr, nullptr, 0, (int)batch, strideD);
     return 0;
@@ -1234,11 +1641,11 @@ static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t 
                 if (grid * warps_per_cta > items) grid = (items + warps_per_cta - 1) / warps_per_cta;
 #define F32_WARP(LPP_, PC_)                                                                                                           \
     {                                                                                                                                 \
-        static bool attr_done = false;                                                                                               \
-        if (!attr_done) {                                                                                                            \
+        static bool attr_done[kMaxDevices] = {};                                                                                     \
+        if (!attr_done[g_ctx.device]) {                                                                                              \
             CUDA_TRY(cudaFuncSetAttribute(fastmul_batched_f32_warp_kernel<LPP_, PC_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                           (int)(200 * 1024)));                                                                      \
-            attr_done = true;                                                                                                        \
+            attr_done[g_ctx.device] = true;                                                                                          \
         }                                                                                                                            \
         fastmul_batched_f32_warp_kernel<LPP_, PC_><<<(unsigned)grid, 32 * warps_per_cta, smem, s>>>(                                  \
             (float*)D, (const float*)A, (const float*)X, (int)M, (int)N, (int)P, batch, strideD, strideA, strideX, slot_floats);     \
@@ -1273,11 +1680,11 @@ static int fastmul_batched_dev(T* D, const T* A, const T* X, int64_t M, int64_t 
     while (G > 1 && G * slot > budget) --G;
     if ((int64_t)G > batch) G = (int)batch;
     const size_t smem = 2 * (size_t)G * slot;
-    static size_t attr_set[2] = {0, 0};
+    static size_t attr_set[kMaxDevices][2] = {};
     const int ti = sizeof(T) == 8 ? 0 : 1;
-    if (smem > 48 * 1024 && smem > attr_set[ti]) {
+    if (smem > 48 * 1024 && smem > attr_set[g_ctx.device][ti]) {
         CUDA_TRY(cudaFuncSetAttribute(fastmul_batched_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-        attr_set[ti] = 220 * 1024;
+        attr_set[g_ctx.device][ti] = 220 * 1024;
     }
     int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
@@ -1410,7 +1817,7 @@ int jblas_b200_d2h(void* dst, const void* src, size_t bytes)
 int jblas_b200_host_register(void* host, size_t bytes)
 {
     if (int rc = require_init()) return rc;
-    CUDA_TRY(cudaHostRegister(host, bytes, cudaHostRegisterDefault));
+    CUDA_TRY(cudaHostRegister(host, bytes, cudaHostRegisterPortable));  // pinned for every GPU of the process (multi-GPU entries)
     return 0;
 }
 int jblas_b200_host_unregister(void* host)
@@ -1535,7 +1942,7 @@ const char* jblas_b200_kernel_name(int kidx) { return (kidx >= 0 && kidx < NUM_K
 int jblas_b200_num_kernels(void) { return NUM_KERNELS; }
 
 int64_t jblas_b200_launch_count(void) { return g_launches.load(); }
-float jblas_b200_time_last_ms(void) { return g_ctx.last_ms; }
+float jblas_b200_time_last_ms(void) { return g_primary >= 0 ? g_ctxs[g_primary].last_ms : 0.f; }
 
 int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms_out)
 {
@@ -1571,6 +1978,7 @@ int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms_out)
         } else if (kind == 6) {  // FFMA2 (fma.rn.f32x2), 8x8 outer-product pattern, 2 CTAs per SM
             probe_ffma2_tile_kernel<<<g_ctx.num_sms * 2, threads, 0, s>>>((float*)out, iters, 1.0000001f, 1e-9f);
             flops = 2.0 * 64 * iters * (double)g_ctx.num_sms * 2 * threads;
+#ifdef JBLAS_B200_TUNING_PROBES
         } else if (kind >= 7 && kind < 7 + 64) {  // FFMA2 inner loop of the exact-FP32 kernel with its shared-memory operand loads (mode = kind - 7)
             const int grid = g_ctx.num_sms * 2;
             switch (kind - 7) {
@@ -1592,9 +2000,10 @@ int jblas_b200_probe_pipe(int kind, int iters, double* tflops, float* ms_out)
                 default: probe_ffma2_lds_kernel<13, 16, 1><<<grid, threads, 0, s>>>((float*)out, iters); break;
             }
             flops = 2.0 * 128 * 16 * iters * (double)grid * threads;
+#endif
         } else {
             cudaFree(out);
-            return fail(JBLAS_B200_EINVAL, "unknown probe kind %d", kind);
+            return fail(JBLAS_B200_EINVAL, "unknown probe kind %d (kinds 7+ exist only in a library built with JBLAS_B200_TUNING_PROBES)", kind);
         }
         g_launches++;
         CUDA_TRY(cudaEventRecord(g_ctx.ev1, s));

@@ -32,6 +32,21 @@
 
 namespace jb {
 
+// a = hi + lo, both exactly representable in TF32: hi = rna(a), lo = rna(a - hi).  Non-finite a travels in hi only.  A FINITE a
+// within half a TF32 ulp of FLT_MAX would round UP to +-Inf (and a - Inf, Inf*x + (-Inf)*x would poison the sum with NaN):
+// there hi is truncated toward zero instead (still TF32-exact, |a - hi| < 1 ulp) and lo carries the rest.
+__device__ __forceinline__ void split_tf32(float a, float& hf, float& lf)
+{
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(a));
+    hf = __uint_as_float(h);
+    if (isfinite(a) && !isfinite(hf)) hf = __uint_as_float(__float_as_uint(a) & 0xffffe000u);  // round toward zero: stays finite
+    float rest = a - hf;  // exact: hi holds the leading bits of a
+    if (!isfinite(a)) rest = 0.f;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(rest));
+    lf = __uint_as_float(l);
+}
+
 // ---- operand split pre-pass: src (rows x cols, ld) -> hi, lo (rows x cols, ld2), both exactly representable in TF32 ----
 __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols, float* __restrict__ hi,
                                   float* __restrict__ lo, int64_t ld2)
@@ -39,15 +54,10 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t lds, in
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     for (int c = blockIdx.y; c < cols; c += gridDim.y) {
-        const float a = src[(size_t)c * lds + r];
-        uint32_t h, l;
-        asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(a));
-        const float hf = __uint_as_float(h);
-        float rest = a - hf;  // exact: hi holds the leading bits of a
-        if (!isfinite(a)) rest = 0.f;  // Inf/NaN travel in the hi part only
-        asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(rest));
+        float hf, lf;
+        split_tf32(src[(size_t)c * lds + r], hf, lf);
         hi[(size_t)c * ld2 + r] = hf;
-        lo[(size_t)c * ld2 + r] = __uint_as_float(l);
+        lo[(size_t)c * ld2 + r] = lf;
     }
 }
 
@@ -66,14 +76,7 @@ __global__ void split_tf32_transpose_kernel(const float* __restrict__ src, int64
             const int r = r0 + tx, c = c0 + ty + 8 * j;
             float hf = 0.f, lf = 0.f;
             if (r < rows && c < cols) {
-                const float a = src[(size_t)c * lds + r];
-                uint32_t h, l;
-                asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(a));
-                hf = __uint_as_float(h);
-                float rest = a - hf;
-                if (!isfinite(a)) rest = 0.f;
-                asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(rest));
-                lf = __uint_as_float(l);
+                split_tf32(src[(size_t)c * lds + r], hf, lf);
             }
             th[ty + 8 * j][tx] = hf;  // [c][r]
             tl[ty + 8 * j][tx] = lf;

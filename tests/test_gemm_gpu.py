@@ -394,7 +394,7 @@ def test_config_tall_skinny_65536x64x64(jb):
     assert ok, worst
 
 
-def _sampled_check(jb, n, dtype_name, selector, exact, extra_rel=0.0):
+def _sampled_check(jb, n, dtype_name, selector, exact, extra_rel=0.0, tiles=()):
     """Full-size run on device-generated inputs; parity on a sampled sub-grid of rows x cols (each element's chain
     is independent) plus a NaN-sentinel sweep and a checksum property over the whole result."""
     import torch
@@ -418,6 +418,18 @@ def _sampled_check(jb, n, dtype_name, selector, exact, extra_rel=0.0):
     else:
         ok, worst = oracle.error_bound_ok(got, want, As, Xs, extra_rel=extra_rel)
         assert ok, worst
+    # whole tiles, not only scattered elements: the 128 x 128 corner tile (matrix edge) and a 128 x 128 window that
+    # straddles a tile seam in both directions (rows/columns 64..191 past a 128-multiple)
+    for r0, c0 in tiles:
+        As = np.asfortranarray(A[r0:r0 + 128, :].cpu().numpy())
+        Xs = np.asfortranarray(X[:, c0:c0 + 128].cpu().numpy())
+        got = np.asfortranarray(D[r0:r0 + 128, c0:c0 + 128].cpu().numpy())
+        want = oracle.oracle_gemm(As, Xs)
+        if exact:
+            assert bits_equal(got, want), (r0, c0)
+        else:
+            ok, worst = oracle.error_bound_ok(got, want, As, Xs, extra_rel=extra_rel)
+            assert ok, (worst, r0, c0)
     # size-independent property: D*1 == A*(X*1) within the reference bound scaled for the extra sum
     ones = torch.ones(n, 1, dtype=torch.float64, device="cuda")
     lhs = D.double() @ ones
@@ -433,8 +445,25 @@ def test_config_8192_cubed_f64_simt_sampled_bit_identical(jb):
     _sampled_check(jb, 8192, "float64", jb.F64_SIMT, exact=True)
 
 
-def test_config_8192_cubed_f64_dmma_sampled_within_bound(jb):
-    _sampled_check(jb, 8192, "float64", jb.F64_DMMA, exact=False)
+def test_config_8192_cubed_f64_dmma_sampled_bit_identical(jb):
+    """The headline kernel (AUTO = dmma_tma_f64_128x128x32_s3).  Its contract is the tolerance; DMMA is MEASURED
+    bit-identical to the chain on B200 (test_dmma_is_bit_identical_to_the_chain_on_b200), so the headline config is
+    held to every bit: scattered sample + the corner tile + a window across a tile seam."""
+    assert jb.plan(8192, 8192, 8192)["kernel"] == "dmma_tma_f64_128x128x32_s3"
+    _sampled_check(jb, 8192, "float64", jb.F64_AUTO, exact=True, tiles=[(8192 - 128, 8192 - 128), (4032, 1984)])
+
+
+def test_config_32768_cubed_f64_sampled_bit_identical(jb):
+    """BASELINE configs[4] on ONE GPU (3 x 8 GiB resident): sampled parity against the oracle chain, corner tile, seam
+    window, NaN-sentinel sweep and the checksum property.  The multi-GPU form of the same config is checked against
+    this single-launch result in tests/test_multigpu_gpu.py and by bench.py's parity_check."""
+    _sampled_check(jb, 32768, "float64", jb.F64_AUTO, exact=True, tiles=[(32768 - 128, 32768 - 128), (16320, 8128)])
+
+
+def test_config_16384_cubed_f32_3xtf32_sampled_within_stated_bound(jb):
+    """BASELINE configs[2], opt-in 3xTF32 path at FULL size: (2*K*2^-23 + 2^-18)*(|A||X|) on the sample and two tiles."""
+    _sampled_check(jb, 16384, "float32", jb.F32_3XTF32, exact=False, extra_rel=2.0 ** -18,
+                   tiles=[(16384 - 128, 16384 - 128), (8128, 4032)])
 
 
 def test_config_16384_cubed_f32_exact_sampled_bit_identical(jb):

@@ -3,6 +3,8 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from jblas.jl_b200 import build as _build
+_build.build(probes=True)  # the ablation probes are not in the shipped library
 import jblas.jl_b200 as jb
 jb.init(0)
 print("ffma2_tile (registers only)", jb.probe_pipe("ffma2_tile", 10000)[0])
