@@ -564,7 +564,7 @@ def run_gpu(args):
             other = [time_other_config(jb, "c4a"), time_other_config(jb, "c4b"), time_other_config(jb, "c3"),
                      time_other_config(jb, "c3", kernel=jb.F32_3XTF32, extra_rel=2.0 ** -18)]
             other[-1]["config"] = "c3_3xtf32"
-        strong_c5 = run_strong_c5(args, jb, dist, dev, world, rank, selector)
+        strong_c5 = run_strong_c5(args, jb, dist, dev, world, rank, selector, cpu_group)
 
     if rank == 0:
         line = {
@@ -590,7 +590,7 @@ def run_gpu(args):
 C5_ONE_GPU_FILE = os.path.join(ROOT, "profiles", "c5_1gpu.json")
 
 
-def run_strong_c5(args, jb, dist, dev, world, rank, selector):
+def run_strong_c5(args, jb, dist, dev, world, rank, selector, cpu_group=None):
     """BASELINE configs[4]: Float64 32768^3, column-sharded over `world` GPUs (strong scaling), A (8 GiB) resident on rank 0
     and delivered in K panels behind the multiplies.  1 warm-up + 3 timed steps, max over ranks, sampled parity per rank.
     `efficiency` = T1 / (world * T_world) with T1 the one-GPU time of the same code: measured in this run when world == 1
@@ -627,7 +627,24 @@ def run_strong_c5(args, jb, dist, dev, world, rank, selector):
     del A, X, D, sg
     torch.cuda.empty_cache()
     flops = 2.0 * n * n * n
-    out = {"workload": WORKLOADS["c5"][4], "n_gpus": world, "steps": steps, "ms_per_step": ms, "tflops": flops / (ms * 1e-3) / 1e12,
+    # the same config END TO END: host A, X, D (3 x 8 GiB, pinned) through the C-ABI host-pointer entry on `world` GPUs of one
+    # process (rank 0 makes the call; at world == 1 it is the plain one-GPU entry).  2 * 8 GiB up and 8 GiB back per call.
+    e2e = None
+    if not args.no_e2e:
+        import numpy as np
+
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            shard = n // world
+            seams = [c for g in range(1, world) for c in (g * shard - 1, g * shard)]
+            sec, h2d, d2h, par = mgpu_host_call(jb, np, "float64", n, n, n, world, selector, 1 if world == 1 else 2, SEED_A, SEED_X, seams)
+            e2e = {"value": flops / sec / 1e12, "unit": "TFLOP/s", "ms_per_step": 1e3 * sec, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "parity_check": par, "api": "jblas_b200_mgpu_gemm_f64, one host process, pinned host matrices" if world > 1 else "jblas_b200_gemm_f64, pinned host matrices"}
+        if world > 1:
+            dist.barrier(group=cpu_group)
+    out = {"workload": WORKLOADS["c5"][4], "n_gpus": world, "steps": steps, "ms_per_step": ms, "tflops": flops / (ms * 1e-3) / 1e12, "e2e": e2e,
            "frac_of_nominal_per_gpu": flops / (ms * 1e-3) / 1e12 / world / FP64_NOMINAL_TFLOPS, "scaling": "strong", "transport": bcast,
            "parity_check": parity}
     if world == 1:
@@ -638,9 +655,99 @@ def run_strong_c5(args, jb, dist, dev, world, rank, selector):
             ref = json.load(open(C5_ONE_GPU_FILE))
             out["t1_ms"], out["t1_source"] = float(ref["ms_per_step"]), "profiles/c5_1gpu.json: " + ref.get("source", "")
             out["efficiency"] = out["t1_ms"] / (world * ms)
+            if e2e is not None and ref.get("e2e_ms_per_step"):
+                out["e2e"]["efficiency"] = float(ref["e2e_ms_per_step"]) / (world * e2e["ms_per_step"])
         except Exception:
             out["efficiency"] = None
     return out
+
+
+def host_link_probe(n_gpus, mib=256, reps=3):
+    """What THIS box's host side can move when `n_gpus` GPUs copy at once from/to pinned host memory (one process, one
+    stream per GPU and direction): GiB/s summed over the GPUs, each direction alone and both together.  It bounds every
+    end-to-end figure that moves A, X and D through host memory -- on the pool's 8-GPU VMs the host side, not the GPUs'
+    own links, is the limit (profiles/r2_pcie_probe_8gpu.txt)."""
+    import torch
+
+    hin = [torch.empty(mib << 20, dtype=torch.uint8).pin_memory() for _ in range(n_gpus)]
+    hout = [torch.empty(mib << 20, dtype=torch.uint8).pin_memory() for _ in range(n_gpus)]
+    din = [torch.empty(mib << 20, dtype=torch.uint8, device=f"cuda:{d}") for d in range(n_gpus)]
+    dout = [torch.empty(mib << 20, dtype=torch.uint8, device=f"cuda:{d}") for d in range(n_gpus)]
+    sin = [torch.cuda.Stream(device=d) for d in range(n_gpus)]
+    sout = [torch.cuda.Stream(device=d) for d in range(n_gpus)]
+
+    def run(h2d, d2h):
+        def once():
+            for d in range(n_gpus):
+                if h2d:
+                    with torch.cuda.stream(sin[d]):
+                        din[d].copy_(hin[d], non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(sout[d]):
+                        hout[d].copy_(dout[d], non_blocking=True)
+            for d in range(n_gpus):
+                torch.cuda.synchronize(d)
+
+        once()
+        t = time.perf_counter()
+        for _ in range(reps):
+            once()
+        return mib / 1024 * n_gpus * reps / (time.perf_counter() - t)
+
+    out = {"gpus": n_gpus, "mib_per_gpu_per_direction": mib, "h2d_only_gibs": run(True, False), "d2h_only_gibs": run(False, True),
+           "each_direction_when_both_gibs": run(True, True)}
+    del hin, hout, din, dout
+    torch.cuda.empty_cache()
+    return out
+
+
+def link_floor_ms(probe, h2d_bytes, d2h_bytes):
+    """Lower bound of one call's transfer time on this box: the better of 'uploads, then downloads' and 'both at once'."""
+    gi = 2.0 ** 30
+    seq = h2d_bytes / gi / probe["h2d_only_gibs"] + d2h_bytes / gi / probe["d2h_only_gibs"]
+    both = max(h2d_bytes, d2h_bytes) / gi / probe["each_direction_when_both_gibs"]
+    return 1e3 * min(seq, both)
+
+
+def mgpu_host_call(jb, np, dtype, M, K, n_total, world, selector, steps, gen_seed_a, gen_seed_x, sample_seams, extra_rel=0.0):
+    """Rank 0 only: the single-process multi-GPU entry of the C ABI on pinned host matrices (what jmul!(D, A, X; gpus = N) hits);
+    returns (seconds per call, h2d bytes, d2h bytes, parity object)."""
+    import torch
+
+    import oracle
+
+    ndt = np.float64 if dtype == "float64" else np.float32
+    chunk = 4096
+    Ah = np.empty((M, K), dtype=ndt, order="F")
+    for c0 in range(0, K, chunk):
+        Ah[:, c0:min(c0 + chunk, K)] = jb.mrandn(M, min(chunk, K - c0), dtype, seed=gen_seed_a, first_col=c0).cpu().numpy()
+    Xh = np.empty((K, n_total), dtype=ndt, order="F")
+    for c0 in range(0, n_total, chunk):  # the one global X (the ranks' shards are column blocks of it), generated on this GPU
+        Xh[:, c0:min(c0 + chunk, n_total)] = jb.mrandn(K, min(chunk, n_total - c0), dtype, seed=gen_seed_x, first_col=c0).cpu().numpy()
+    Dh = np.full((M, n_total), np.nan, dtype=ndt, order="F")
+    torch.cuda.empty_cache()
+    with jb.pinned(Ah, Xh, Dh):
+        jb.jmul_(Dh, Ah, Xh, kernel=selector, gpus=world)  # warm-up: per-GPU contexts, workspaces, peer access
+        t = time.perf_counter()
+        for _ in range(steps):
+            jb.jmul_(Dh, Ah, Xh, kernel=selector, gpus=world)
+        sec = (time.perf_counter() - t) / steps
+    assert not np.isnan(Dh).any(), "NaN sentinel survived in the multi-GPU host result"
+    # parity of the end-to-end result (checker, after the timed region): sampled rows x columns of the host D, the columns on
+    # both sides of every GPU's shard seam included, against the oracle chain on the same host bits
+    rng = np.random.Generator(np.random.PCG64(7))
+    rows = np.unique(np.concatenate([[0, 1, M - 2, M - 1], rng.integers(0, M, 20)]))
+    cols = np.unique(np.concatenate([[0, n_total - 1], sample_seams, rng.integers(0, n_total, 10)]).astype(np.int64))
+    As, Xs = np.asfortranarray(Ah[rows, :]), np.asfortranarray(Xh[:, cols])
+    want = oracle.oracle_gemm(As, Xs)
+    got = np.asfortranarray(Dh[np.ix_(rows, cols)])
+    ok, worst = oracle.error_bound_ok(got, want, As, Xs, extra_rel=extra_rel)
+    assert ok, f"multi-GPU end-to-end result outside the tolerance: {worst}"
+    parity = {"rows": int(rows.size), "cols": int(cols.size), "shard_seams_sampled": len(sample_seams), "bit_identical": bool(got.tobytes() == want.tobytes()),
+              "within_bound": bool(ok), "worst_err_over_bound": float(worst)}
+    h2d, d2h = int(Ah.nbytes + Xh.nbytes), int(Dh.nbytes)
+    del Ah, Xh, Dh
+    return sec, h2d, d2h, parity
 
 
 def run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_step, selector, cpu_group=None):
@@ -682,31 +789,18 @@ def run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_st
     torch.cuda.synchronize()
     dist.barrier(group=cpu_group)
     if rank == 0:
-        ndt = np.float64 if dtype == "float64" else np.float32
-        Ah = np.asfortranarray(A.cpu().numpy())
-        Xh = np.empty((K, n_total), dtype=ndt, order="F")
-        chunk = 4096
-        for c0 in range(0, n_total, chunk):  # the one global X (the ranks' shards are column blocks of it), generated on this GPU
-            c1 = min(c0 + chunk, n_total)
-            Xh[:, c0:c1] = jb.mrandn(K, c1 - c0, dtype, seed=SEED_X, first_col=c0).cpu().numpy()
-        Dh = np.full((M, n_total), np.nan, dtype=ndt, order="F")
-        torch.cuda.empty_cache()
-        with jb.pinned(Ah, Xh, Dh):
-            jb.jmul_(Dh, Ah, Xh, kernel=selector, gpus=world)  # warm-up: per-GPU contexts, workspaces, peer access
-            t = time.perf_counter()
-            for _ in range(steps):
-                jb.jmul_(Dh, Ah, Xh, kernel=selector, gpus=world)
-            sec = time.perf_counter() - t
-        assert not np.isnan(Dh).any(), "NaN sentinel survived in the multi-GPU host result"
-        # parity of the end-to-end result: rank 0's own device-resident shard D (already checked against the oracle above) is
-        # the first column block of the same product
-        same = bool(np.array_equal(Dh[:, :sg.shard_cols], D.cpu().numpy()))
-        result[0] = {"value": flops_step * steps / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(Ah.nbytes + Xh.nbytes),
-                     "d2h_bytes_per_step": int(Dh.nbytes), "steps": steps, "ms_per_step": 1e3 * sec / steps,
-                     "first_shard_equals_device_resident_result": same,
+        seams = [c for g in range(1, world) for c in (g * sg.shard_cols - 1, g * sg.shard_cols)]
+        sec, h2d, d2h, parity = mgpu_host_call(jb, np, dtype, M, K, n_total, world, selector, steps, SEED_A, SEED_X, seams,
+                                               extra_rel=(2.0 ** -18 if args.kernel == "tf32x3" else 0.0))
+        probe = host_link_probe(world)
+        floor = link_floor_ms(probe, h2d, d2h)
+        result[0] = {"value": flops_step / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+                     "ms_per_step": 1e3 * sec, "parity_check": parity,
+                     "host_link_probe": probe, "host_link_floor_ms": floor, "frac_of_host_link_floor": floor / (1e3 * sec),
+                     "note": "host_link_floor_ms = the time this box's host side needs just to move the step's H2D and D2H bytes with all "
+                             f"{world} GPUs copying at once (measured in this run); when it exceeds the compute time the end-to-end figure is bound by the host, not by the GPUs",
                      "api": f"jblas_b200_mgpu_gemm_{'f64' if dtype == 'float64' else 'f32'} (ONE host process, host pointers pinned by jblas_b200_host_register, "
                             f"{world} GPUs: A slices over every GPU's own PCIe link + NVLink peer pulls, X / D column blocks per GPU; wall clock around the call)"}
-        del Ah, Xh, Dh
     dist.barrier(group=cpu_group)
     return result[0]
 

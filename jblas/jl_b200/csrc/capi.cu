@@ -575,7 +575,13 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
     out->tiles_m = (int)((M + k.bm - 1) / k.bm);
     out->tiles_n = (int)((N + k.bn - 1) / k.bn);
     // raster group: keep ~sqrt(#SMs) tile rows together so a resident wave touches a near-square block
-    out->group_m = out->tiles_m < 12 ? out->tiles_m : 12;
+    static int group_override = -1;  // JBLAS_B200_GROUP_M: raster experiments (DRAM traffic vs group height, profiles/r2_group_m_sweep.txt)
+    if (group_override < 0) {
+        const char* e = getenv("JBLAS_B200_GROUP_M");
+        group_override = e ? atoi(e) : 0;
+    }
+    const int want_group = group_override > 0 ? group_override : 12;
+    out->group_m = out->tiles_m < want_group ? out->tiles_m : want_group;
     if (out->group_m < 1) out->group_m = 1;
     return 0;
 }
@@ -1008,10 +1014,17 @@ static int gemm_host_issue(int dtype, T* D, const T* A, const T* X, int64_t M, i
         if (kp > K) kp = K;
     }
     const int64_t kfirst = (kp < K && kp >= 1024) ? kp / 4 : (kp < K && kp >= 512 ? 256 : kp);
-    // phase-1 columns: everything for small problems, otherwise the first half (multiple of 128)
+    // phase-1 columns: everything for small problems, otherwise the first half (multiple of 128) on one GPU.  Phase 1 exists
+    // to keep the tensor pipe busy while A is on its way, and with G GPUs every link carries only 1/G of A: the phase-1 share
+    // shrinks with G (half / G, at least 256 columns), so that A is complete early, the column-block phase with its
+    // overlapped D2H starts early, and D -- the transfer that saturates the host side first when several GPUs write to one
+    // host (measured: 8 GPUs, profiles/r2_pcie_probe_8gpu.txt) -- starts to flow back as soon as possible.
     for (int g = 0; g < G; ++g) {
         dv[g].N1 = dv[g].ns;
-        if (big && (size_t)M * dv[g].ns * es > panel_bytes && dv[g].ns >= 512) dv[g].N1 = ((dv[g].ns / 2) + 127) / 128 * 128;
+        if (big && (size_t)M * dv[g].ns * es > panel_bytes && dv[g].ns >= 512) {
+            dv[g].N1 = ((dv[g].ns / 2 / G) + 127) / 128 * 128;
+            if (dv[g].N1 < 256) dv[g].N1 = 256;
+        }
     }
     // phase-2 column blocks: ~64 MiB of D each
     int64_t nb = (int64_t)(panel_bytes / ((size_t)M * es));

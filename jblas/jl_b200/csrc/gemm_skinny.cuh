@@ -1,0 +1,268 @@
+// gemm_skinny.cuh -- tall-skinny FP64 product D(M x N) = A(M x K) * X(K x N) with N <= 64 and a short K:
+// X stays RESIDENT in shared memory, A is streamed from HBM exactly once, D is written exactly once.
+//
+// Regime (BASELINE configs[3], 65536 x 64 x 64): 8 flop per byte -- the FP64 pipe (14.4 us) and HBM (10.3 us) bind almost
+// together, so neither may idle.  The reference's analogue is fastmul!'s thin panel (src/kernels.jl:202-208): the whole X
+// is small, A is a tall stack of row blocks.  A tile kernel is the wrong shape for it (K = 64 is two pipeline stages; every
+// 64 x 32 tile pays a pipeline fill, an mbarrier round trip between warps and re-fetches its X block: 25-27 us,
+// profiles/r1_ncu_dmma_tma_skinny_*).
+//
+// Design: ONE WARP owns one 16-row block of D for all N columns (2 row tiles x NI column tiles of mma.m8n8k4) and runs its
+// own private pipeline -- there is no CTA-wide synchronisation after start-up and no producer warp:
+//   * lane 0 of the warp issues ONE TMA box (16 rows x 64 k = 8 KiB) per (block, k chunk) into one of the warp's two private
+//     shared-memory buffers, completion on the warp's own mbarrier; the box for the NEXT item is in flight while the current
+//     one is multiplied (8 warps x 2 x 8 KiB = 128 KiB of loads outstanding per SM, no register cost).  TMA zero-fills
+//     rows >= M.
+//   * the two 8-row tiles are INTERLEAVED (tile mi holds rows 2g + mi): lane (g, t) reads rows (2g, 2g+1) of column 4s + t
+//     with one LDS.128 and later writes rows (2g, 2g+1) of a D column with one 16-byte store -- 8 lanes cover a full
+//     128-byte line, D is written straight from the accumulators.
+//   * bank conflicts: an LDS.128 is served a quarter-warp at a time (g in {2q, 2q+1}, t in 0..3): its eight 16-byte chunks
+//     must differ.  A is therefore described to TMA as a 4-D tensor (m, s_lo, t, s_hi) with k = 8 s_hi + 4 s_lo + t, box
+//     {16, 2, 4, 8}: the 128-byte row of k-step s, lane column t lands at row 8 (s >> 1) + 2t + (s & 1), and the hardware
+//     128B swizzle XORs the chunk index g with (row & 7) = 2t + (s & 1) -- g ^ 2t is distinct over a quarter-warp.
+//   * X fragments come from shared memory, staged once per CTA with cp.async in FRAGMENT-MAJOR order (the 32 lane values of
+//     one fragment are contiguous: conflict-free, and every load is one base register + an immediate); k >= K is -0.0 on the X
+//     side (and 0 on the A side), so a padded product is -0.0 and leaves every accumulator untouched.
+//   * fragments are double-buffered in registers one k-step ahead, which also pins the issue order: 16 independent DMMAs per
+//     step (ptxas otherwise chains the steps of one accumulator back to back and stalls on the DMMA latency: measured 46 %
+//     tensor pipe with register-resident A).
+//   * accumulators start at -0.0 (or C): ascending k, 4 per DMMA -> bit-identical to the reference chain on B200.
+// Blocks are dealt round-robin over ALL warps of the grid with the CTA index fastest, so the blocks in flight at any moment
+// are neighbours in memory and every SM sub-partition gets the same count (+-1).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+#include "gemm_dmma_tma.cuh"
+
+namespace jb {
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+template <int NI_, int WARPS_, int KC_ = 64, int EXP_ = 0>
+struct SkinnyCfg {
+    static constexpr bool TWO_ACC = false;
+    static constexpr int EXP = EXP_;  // development experiments (tools/skinny_probe): 1 = no stores, 2 = every chunk has KC/4 steps (compile-time trip count)
+    static constexpr int NI = NI_, WARPS = WARPS_, THREADS = WARPS_ * 32, BN = NI_ * 8;
+    static constexpr int KC = KC_;                    // k chunk of one TMA box (multiple of 8)
+    static constexpr int BOX_BYTES = 16 * KC * 8;     // 16 rows x KC columns of doubles
+    static constexpr int NBUF = 2;
+    static_assert(KC_ % 8 == 0 && BOX_BYTES % 1024 == 0, "a box is a whole number of swizzle atoms");
+    // X lives in shared memory FRAGMENT-MAJOR, sX[s][n][t]: the 32 doubles lane (g, t) = X[4s + t][8 ni + g] of k-step s, column
+    // tile ni are contiguous in lane order, so every fragment load is base + lane*8 + immediate (conflict-free)
+    static size_t x_bytes(int K) { return (size_t)(K / 4) * NI * 256; }
+    static size_t smem(int K) { return (size_t)WARPS * NBUF * BOX_BYTES + x_bytes(K) + (WARPS * NBUF + 1) * sizeof(uint64_t) + 1024; }
+};
+
+template <typename Cfg, bool ACC>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX, double* __restrict__ D, int M, int N, int K,
+                       int64_t ldd, const double* __restrict__ Cin, int64_t ldc, unsigned long long* trace = nullptr)
+{
+    // development aid (tools/skinny_probe): per-warp %globaltimer stamps -- [0] entry, [1] X staged, [2] first box landed, [3+i] block i stored
+    auto stamp = [&](int slot) {
+        if (trace && (threadIdx.x & 31) == 0 && slot < 12) {
+            unsigned long long tns;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+            trace[((size_t)blockIdx.x * Cfg::WARPS + (threadIdx.x >> 5)) * 12 + slot] = tns;
+        }
+    };
+    stamp(0);
+    constexpr int NI = Cfg::NI, KC = Cfg::KC, NBUF = Cfg::NBUF;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // swizzle atoms
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    unsigned char* myA = base + (size_t)warp * NBUF * Cfg::BOX_BYTES;                                 // this warp's two boxes
+    double* sX = reinterpret_cast<double*>(base + (size_t)Cfg::WARPS * NBUF * Cfg::BOX_BYTES);
+    const int ksteps = K >> 2;  // K % 8 == 0 (host-checked): whole pairs of k-steps
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + (size_t)ksteps * NI * 32);
+    uint64_t* full = bars + warp * NBUF;
+
+    const int nblocks = (M + 15) >> 4, nchunks = (K + KC - 1) / KC;
+    const int total_warps = gridDim.x * Cfg::WARPS;
+    const int first = warp * gridDim.x + blockIdx.x;  // CTA index fastest: every SM sub-partition gets the same number of blocks (+-1)
+
+    // ---- X first: ONE 3-D TMA box (t, n, s) -> sX[s][n][t], which is fragment-major: the 32 lane values X[4s + t][8 ni + g] of
+    //      a fragment are contiguous in lane order (conflict-free, address = base + immediate).  Columns n >= N are zero-filled
+    //      by TMA (their accumulators are never stored).  It is requested before any A box so that it is not queued behind
+    //      the start-up burst of A requests. ----
+    uint64_t* xbar = bars + Cfg::WARPS * NBUF;
+    if (tid == 0) {
+        mbar_init(xbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(xbar, (uint32_t)(ksteps * Cfg::BN * 32));
+        tma_load_3d_hint(sX, &mapX, xbar, 0, 0, 0, kL2EvictLast);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    // item i of this warp = (block first + (i / nchunks) * total_warps, chunk i % nchunks)
+    auto issue = [&](int blk, int chunk, int buf) {
+        if (lane == 0) {
+            mbar_expect_tx(&full[buf], Cfg::BOX_BYTES);
+            tma_load_4d(myA + buf * Cfg::BOX_BYTES, &mapA, &full[buf], blk * 16, 0, 0, chunk * (KC / 8));
+        }
+    };
+    int iblk = first, ichunk = 0;  // next item to ISSUE
+    auto advance = [&](int& blk, int& chunk) {
+        if (++chunk == nchunks) { chunk = 0; blk += total_warps; }
+    };
+#pragma unroll
+    for (int b = 0; b < NBUF; ++b) {
+        if (iblk < nblocks) issue(iblk, ichunk, b);
+        advance(iblk, ichunk);
+    }
+    __syncthreads();  // xbar is initialised for everybody
+    mbar_wait(xbar, 0);
+    stamp(1);
+
+    const uint32_t sB = smem_u32(sX + lane);                    // + ((k0/4 + s) * NI + ni) * 256
+    // rows (2g, 2g+1) of column k = 4s + t of a box: row R = 8 (s >> 1) + 2t + (s & 1), chunk g ^ (R & 7)
+    const uint32_t sA0 = smem_u32(myA);
+    const uint32_t offA[2] = {(uint32_t)((2 * t) * 128 + ((g ^ (2 * t)) << 4)), (uint32_t)((2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4))};
+    // Fast paths (warp-uniform): a block whose 16 rows all exist, all BN columns exist and whose D (and C) columns are 16-byte
+    // aligned moves through pointer increments only -- the general path costs ~430 instructions per block, and with every warp
+    // of an SM sub-partition reaching its epilogue at the same moment that time is NOT hidden (measured: 26 % of the kernel).
+    const bool vec_ok = N == Cfg::BN && (ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 &&
+                        (!ACC || ((ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(Cin) & 15) == 0));
+    const int64_t col0 = 2 * t;  // this lane's first column; the others are col0 + 8 ni + c
+
+    int blk = first, buf = 0, done = 0;
+    uint32_t phase = 0;
+    // One block of D: all k chunks, then the stores.  Called alternately with TWO accumulator sets: the stores of a block read
+    // their registers asynchronously, and re-initialising the same registers for the next block would wait for them.
+    auto process = [&](double (&acc)[2][NI][2]) {
+        const int m = blk * 16 + 2 * g;
+        const bool fast = vec_ok && blk * 16 + 16 <= M;
+        if constexpr (ACC) {
+            if (fast) {
+                const double* p = Cin + col0 * ldc + m;
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const double2 v = *reinterpret_cast<const double2*>(p + (int64_t)(ni * 8 + c) * ldc);
+                        acc[0][ni][c] = v.x;
+                        acc[1][ni][c] = v.y;
+                    }
+            } else {
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int n = ni * 8 + 2 * t + c;
+                        double2 v = make_double2(0.0, 0.0);
+                        if (n < N) {
+                            const double* p = Cin + (size_t)n * ldc + m;
+                            if (m < M) v.x = p[0];
+                            if (m + 1 < M) v.y = p[1];
+                        }
+                        acc[0][ni][c] = v.x;
+                        acc[1][ni][c] = v.y;
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) acc[0][ni][c] = acc[1][ni][c] = -0.0;
+        }
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            mbar_wait(&full[buf], phase);
+            if (done == 0 && chunk == 0) stamp(2);
+            const int s0 = chunk * (KC / 4);
+            const int steps = (Cfg::EXP & 2) ? KC / 4 : min(ksteps - s0, KC / 4);  // even: K % 8 == 0
+            const uint32_t pa = sA0 + buf * Cfg::BOX_BYTES, pb = sB + s0 * NI * 256;
+            double2 a[2];
+            double b[2][NI];
+            auto load = [&](int s, int which) {
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(a[which].x), "=d"(a[which].y) : "r"(pa + offA[which] + (s >> 1) * 1024));
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni) b[which][ni] = lds_f64(pb + (s * NI + ni) * 256);
+            };
+            auto mma = [&](int which) {
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni) {
+                    dmma884(acc[0][ni][0], acc[0][ni][1], a[which].x, b[which][ni]);
+                    dmma884(acc[1][ni][0], acc[1][ni][1], a[which].y, b[which][ni]);
+                }
+            };
+            load(0, 0);
+            if constexpr (Cfg::EXP & 2) {
+#pragma unroll
+                for (int s = 0; s < KC / 4; s += 2) {
+                    load(s + 1, 1);
+                    mma(0);
+                    if (s + 2 < KC / 4) load(s + 2, 0);
+                    mma(1);
+                }
+            } else {
+#pragma unroll 2
+                for (int s = 0; s < steps; s += 2) {
+                    load(s + 1, 1);
+                    mma(0);
+                    if (s + 2 < steps) load(s + 2, 0);
+                    mma(1);
+                }
+            }
+            __syncwarp();  // every lane has read the box: it may be overwritten
+            if (iblk < nblocks) issue(iblk, ichunk, buf);
+            advance(iblk, ichunk);
+            if (++buf == NBUF) { buf = 0; phase ^= 1; }
+        }
+        if constexpr (Cfg::EXP & 1) {
+            double sum = 0;
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) sum += acc[0][ni][c] * acc[1][ni][c];
+            if (sum == 1.2345678) D[m] = sum;
+        } else if (fast) {
+            double* p = D + col0 * ldd + m;
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    *reinterpret_cast<double2*>(p + (int64_t)(ni * 8 + c) * ldd) = make_double2(acc[0][ni][c], acc[1][ni][c]);
+        } else {
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int n = ni * 8 + 2 * t + c;
+                    if (n >= N) continue;
+                    double* p = D + (size_t)n * ldd + m;
+                    if (m < M) p[0] = acc[0][ni][c];
+                    if (m + 1 < M) p[1] = acc[1][ni][c];
+                }
+        }
+        stamp(3 + done);
+        ++done;
+        blk += total_warps;
+    };
+    if constexpr (Cfg::TWO_ACC) {
+        double accA[2][NI][2], accB[2][NI][2];
+        while (blk < nblocks) {
+            process(accA);
+            if (blk >= nblocks) break;
+            process(accB);
+        }
+    } else {
+        double acc[2][NI][2];
+        while (blk < nblocks) process(acc);
+    }
+}
+
+}  // namespace jb
