@@ -21,6 +21,7 @@
 #include "fastmul_batched.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_dmma_tma.cuh"
+#include "gemm_f32_tma.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_simt_f32x2.cuh"
 #include "gemm_tf32x3.cuh"
@@ -255,17 +256,17 @@ static int get_encode_tiled()
 
 // 2-D column-major operand: dim0 = rows (contiguous), dim1 = cols (stride ld elements); box = box_r x box_c, 128B swizzle
 static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esize, uint64_t rows, uint64_t cols,
-                        uint64_t ld, uint32_t box_r, uint32_t box_c)
+                        uint64_t ld, uint32_t box_r, uint32_t box_c, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
 {
     // cuTensorMapEncodeTiled costs 1-2 us, as much as the launch itself on small problems: callers that multiply the same
     // buffers again (every benchmark loop, every K panel of a pipeline) hit a small per-thread cache of encoded maps.
     // A tensor map is a pure function of these eight values, so a stale entry cannot exist.
-    struct Entry { const void* base; uint64_t rows, cols, ld; uint32_t box_r, box_c; int dt, esize; bool valid; CUtensorMap map; };
+    struct Entry { const void* base; uint64_t rows, cols, ld; uint32_t box_r, box_c; int dt, esize, swizzle; bool valid; CUtensorMap map; };
     static thread_local Entry cache[8] = {};
     static thread_local unsigned next_slot = 0;
     for (const Entry& e : cache)
         if (e.valid && e.base == base && e.rows == rows && e.cols == cols && e.ld == ld && e.box_r == box_r && e.box_c == box_c &&
-            e.dt == (int)dt && e.esize == esize) {
+            e.dt == (int)dt && e.esize == esize && e.swizzle == (int)swizzle) {
             *map = e.map;
             return 0;
         }
@@ -275,12 +276,11 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType 
     cuuint32_t box[2] = {box_r, box_c};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(JBLAS_B200_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     Entry& slot = cache[next_slot++ % 8];
     slot.base = base; slot.rows = rows; slot.cols = cols; slot.ld = ld; slot.box_r = box_r; slot.box_c = box_c;
-    slot.dt = (int)dt; slot.esize = esize; slot.map = *map; slot.valid = true;
+    slot.dt = (int)dt; slot.esize = esize; slot.swizzle = (int)swizzle; slot.map = *map; slot.valid = true;
     return 0;
 }
 
@@ -329,6 +329,26 @@ static int launch_dmma_tma(void* D, const void* A, const void* X, int M, int N, 
     gemm_dmma_tma_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mapA, mapX, (double*)D, M, N, K, ldd, tiles_m, tiles_n,
                                                                            group_m, pa, px, ctr, (const double*)Cin, ldc);
     return 0;
+}
+template <typename Cfg, bool ACC>
+static int launch_f32_tma(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                          int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
+{
+    CUtensorMap mapA, mapX;
+    if (int rc = make_tmap_2d(&mapA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)K, (uint64_t)lda, Cfg::BM, Cfg::BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+    if (int rc = make_tmap_2d(&mapX, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)N, (uint64_t)ldx, Cfg::BK, Cfg::BN)) return rc;
+    int grid = tiles_m * tiles_n;
+    if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
+    gemm_f32_tma_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mapA, mapX, (float*)D, M, N, K, ldd, tiles_m, tiles_n, group_m, tile_counter_for(s),
+                                                                          (const float*)Cin, ldc);
+    return 0;
+}
+template <typename Cfg>
+static cudaError_t attr_f32_tma()
+{
+    cudaError_t e = cudaFuncSetAttribute(gemm_f32_tma_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gemm_f32_tma_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
 }
 static int launch_needs_alignment(void*, const void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, int, int,
                                   cudaStream_t, const void*, int64_t)
@@ -426,6 +446,14 @@ static cudaError_t attr_dmma_tma()
             attr_dmma_tma<CFG>, nullptr                                                                            \
     }
 
+#define F32_TMA_ENTRY(NAME, CFG, EFF)                                                                              \
+    {                                                                                                              \
+        NAME, JBLAS_B200_DT_F32, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
+            true, true, 1,                                                                                         \
+            {{launch_needs_alignment, launch_needs_alignment}, {launch_f32_tma<CFG, false>, launch_f32_tma<CFG, true>}}, \
+            attr_f32_tma<CFG>, nullptr                                                                             \
+    }
+
 //                         T      WM WN BK ST MINB
 using S64_128x128 = SimtCfg<double, 2, 4, 16, 4, 1>;
 using S64_128x64 = SimtCfg<double, 2, 2, 16, 4, 1>;
@@ -452,6 +480,7 @@ using T64_64x32_x2 = DmmaTmaCfg<2, 2, 4, 2, 2, 4, 2>;  // 4 warps of 32x16, 2 CT
 using F2_64x64_w4 = F32x2Cfg<2, 2, 1, 8, 16, 4, 4>;  // 4 warps of 32x32 (thread 4x8)
 using F2_64x32_w4 = F32x2Cfg<2, 2, 1, 4, 16, 4, 4>;  // 4 warps of 32x16 (thread 4x4)
 using F2_32x32_w2 = F32x2Cfg<1, 2, 1, 4, 16, 4, 8>;  // 2 warps of 32x16
+using F32T_s4 = F32TmaCfg<4>;          // 128 x 256 x 32, 4 stages of 48 KiB
 using X3_128x256 = Tf32x3Cfg<256, 2>;  // 2 stages of 96 KiB, two 256-column TMEM accumulators
 using X3_128x128 = Tf32x3Cfg<128, 3>;  // 3 stages of 64 KiB
 
@@ -485,6 +514,7 @@ static const KernelInfo g_kernels[] = {
     /* 25 */ SIMT_F32X2_ENTRY("simt_f32x2_64x64x16_w4", F2_64x64_w4, 1.125f),
     /* 26 */ SIMT_F32X2_ENTRY("simt_f32x2_64x32x16_w4", F2_64x32_w4, 1.00f),
     /* 27 */ SIMT_F32X2_ENTRY("simt_f32x2_32x32x16_w2", F2_32x32_w2, 1.00f),
+    /* 28 */ F32_TMA_ENTRY("simt_f32_tma_ffma2_128x256x32_s4", F32T_s4, 1.40f),
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
 static int g_occ[NUM_KERNELS] = {0};  // measured residency (filled at init); 0 = unknown, the planner uses ctas_per_sm
