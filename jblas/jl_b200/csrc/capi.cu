@@ -163,6 +163,7 @@ struct KernelInfo {
     LaunchFn launch[2][2];  // [aligned][acc]
     cudaError_t (*set_attr)();
     int (*query_occ)();  // non-persistent kernels: CTAs of the aligned variant the hardware keeps resident per SM
+    bool has_ragged = false;  // needs_aligned kernels only: launch[0][*] is an element-wise staging variant, not an error
 };
 template <typename K>
 static int occupancy_of(K kernel, int threads, size_t smem)
@@ -350,6 +351,28 @@ static cudaError_t attr_f32_tma()
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(gemm_f32_tma_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
 }
+// The same kernel with element-wise staging (RAGGED): operands whose base or leading dimension is not 16-byte aligned.
+template <typename Cfg, bool ACC>
+static int launch_dmma_tma_ragged(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                                  int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
+{
+    static const CUtensorMap none = {};
+    int grid = tiles_m * tiles_n;
+    if (grid > g_ctx.num_sms * Cfg::MIN_BLOCKS) grid = g_ctx.num_sms * Cfg::MIN_BLOCKS;
+    gemm_dmma_tma_kernel<Cfg, ACC, false, true><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(none, none, (double*)D, M, N, K, ldd, tiles_m, tiles_n, group_m,
+                                                                                        kL2EvictNormal, kL2EvictNormal, nullptr, (const double*)Cin, ldc, 1, 0,
+                                                                                        (const double*)A, (const double*)X, lda, ldx);
+    return 0;
+}
+template <typename Cfg>
+static cudaError_t attr_dmma_tma_ragged()
+{
+    cudaError_t e = cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    return e;
+}
 static int launch_needs_alignment(void*, const void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, int, int,
                                   cudaStream_t, const void*, int64_t)
 {
@@ -446,6 +469,15 @@ static cudaError_t attr_dmma_tma()
             attr_dmma_tma<CFG>, nullptr                                                                            \
     }
 
+// TMA kernels whose warp tile is small enough to also come with the element-wise (RAGGED) producers: unaligned operands take
+// launch[0][*] = the ragged variant instead of an error
+#define DMMA_TMA_RAGGED_ENTRY(NAME, CFG, EFF)                                                                      \
+    {                                                                                                              \
+        NAME, JBLAS_B200_DT_F64, FAM_DMMA, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
+            true, true, CFG::MIN_BLOCKS,                                                                           \
+            {{launch_dmma_tma_ragged<CFG, false>, launch_dmma_tma_ragged<CFG, true>}, {launch_dmma_tma<CFG, false>, launch_dmma_tma<CFG, true>}}, \
+            attr_dmma_tma_ragged<CFG>, nullptr, true                                                               \
+    }
 #define F32_TMA_ENTRY(NAME, CFG, EFF)                                                                              \
     {                                                                                                              \
         NAME, JBLAS_B200_DT_F32, FAM_SIMT, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF,   \
@@ -504,13 +536,13 @@ static const KernelInfo g_kernels[] = {
     /* 15 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4", T64_128x64, 1.02f),
     /* 16 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4", T64_96x64, 1.01f),
     /* 17 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x64_s3", T64_64x64_k64, 1.01f),
-    /* 18 */ DMMA_TMA_ENTRY("dmma_tma_f64_96x64x32_s4_w8", T64_96x64_w8, 1.17f),
-    /* 19 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.14f),
-    /* 20 */ DMMA_TMA_ENTRY("dmma_tma_f64_128x64x32_s4_w8", T64_128x64_w8, 1.185f),
+    /* 18 */ DMMA_TMA_RAGGED_ENTRY("dmma_tma_f64_96x64x32_s4_w8", T64_96x64_w8, 1.17f),
+    /* 19 */ DMMA_TMA_RAGGED_ENTRY("dmma_tma_f64_64x64x32_s3_x2", T64_64x64_x2, 1.14f),
+    /* 20 */ DMMA_TMA_RAGGED_ENTRY("dmma_tma_f64_128x64x32_s4_w8", T64_128x64_w8, 1.185f),
     /* 21 */ TF32X3_ENTRY("tf32x3_tcgen05_f32_128x256x32_s2", X3_128x256, 1.00f),
     /* 22 */ TF32X3_ENTRY("tf32x3_tcgen05_f32_128x128x32_s3", X3_128x128, 0.80f),
-    /* 23 */ DMMA_TMA_ENTRY("dmma_tma_f64_32x32x64_s3_x2", T64_32x32_x2, 1.06f),
-    /* 24 */ DMMA_TMA_ENTRY("dmma_tma_f64_64x32x32_s4_x2", T64_64x32_x2, 1.125f),
+    /* 23 */ DMMA_TMA_RAGGED_ENTRY("dmma_tma_f64_32x32x64_s3_x2", T64_32x32_x2, 1.06f),
+    /* 24 */ DMMA_TMA_RAGGED_ENTRY("dmma_tma_f64_64x32x32_s4_x2", T64_64x32_x2, 1.125f),
     /* 25 */ SIMT_F32X2_ENTRY("simt_f32x2_64x64x16_w4", F2_64x64_w4, 1.125f),
     /* 26 */ SIMT_F32X2_ENTRY("simt_f32x2_64x32x16_w4", F2_64x32_w4, 1.00f),
     /* 27 */ SIMT_F32X2_ENTRY("simt_f32x2_32x32x16_w2", F2_32x32_w2, 1.00f),
@@ -569,7 +601,7 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
     for (int i = 0; i < NUM_KERNELS; ++i) {
         const KernelInfo& k = g_kernels[i];
         if (explicit_idx >= 0 ? (i != explicit_idx) : (k.dtype != dtype || k.family != family)) continue;
-        if (explicit_idx < 0 && k.needs_aligned && !out->aligned) continue;
+        if (explicit_idx < 0 && k.needs_aligned && !out->aligned && !k.has_ragged) continue;
         int64_t tiles = ((M + k.bm - 1) / k.bm) * ((N + k.bn - 1) / k.bn);
         double per_tile = (double)k.bm * k.bn;
         // rounds of resident CTAs; CTAs that share an SM (ctas_per_sm > 1) also share its pipes, so a round of c
@@ -597,6 +629,7 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
             if (rem) t += per_tile * (double)rem / sm_rate((int)rem * warps);
         }
         t /= k.eff;
+        if (k.needs_aligned && !out->aligned) t *= 1.05;  // element-wise staging: measured 5 % slower than the TMA boxes (1023 x 777 x 4097 vs 1024 x 776 x 4096)
         if (best < 0 || t < best_t) { best = i; best_t = t; }
     }
     if (best < 0) return fail(JBLAS_B200_EUNSUPPORTED, "no kernel for this dtype/selector");
@@ -719,6 +752,23 @@ static int set_all_attrs()
     return 0;
 }
 
+// Misaligned operands (base or leading dimension off the 16-byte grid): when is a re-aligned scratch copy worth it?
+//   * Float64 on the tensor pipe (AUTO / DMMA): products up to 3e10 flop run the RAGGED variants of the persistent kernels
+//     (element-wise staging inside the kernel, no extra HBM pass and no scratch: 1023 x 777 x 4097 243 -> 235 us; the staging costs ~5 %, a copy pass less than that only beyond ~3e10 flop); beyond that the 128 x 128
+//     TMA kernel wins by more than the copy costs (< 1 % of such a product);
+//   * exact SIMT families and Float32: from 1e9 flop (their element-wise cp.async variants stage from every thread);
+//   * an explicitly forced kernel: only if it cannot stage element-wise itself.
+static bool wants_realign(int dtype, int selector, double flops)
+{
+    if (selector >= JBLAS_B200_EXPLICIT_BASE) {
+        const int i = selector - JBLAS_B200_EXPLICIT_BASE;
+        if (i < NUM_KERNELS && g_kernels[i].has_ragged) return false;
+        return flops >= 1.0e9;
+    }
+    if (dtype == JBLAS_B200_DT_F64 && (selector == JBLAS_B200_F64_AUTO || selector == JBLAS_B200_F64_DMMA)) return flops >= 3.0e10;
+    return flops >= 1.0e9;
+}
+
 // The general device-side product:  D = A*(X [+ Xadd]) [+ Cin].
 //   Cin  == nullptr : overwrite (jmul!/initkernel!);  Cin == D : D += A*X (kernel!, src/kernels.jl:226);  any other Cin: the
 //                     planned fused form D = A*X + C -- every element's chain starts from C[i,j] instead of -0.0;
@@ -775,7 +825,7 @@ static int gemm_dev_ex(int dtype, T* D, const T* A, const T* X, int64_t M, int64
     const bool splits_itself = dtype == JBLAS_B200_DT_F32 && (selector == JBLAS_B200_F32_3XTF32 ||
                                                                (selector >= JBLAS_B200_EXPLICIT_BASE && selector - JBLAS_B200_EXPLICIT_BASE < NUM_KERNELS &&
                                                                 g_kernels[selector - JBLAS_B200_EXPLICIT_BASE].family == FAM_TF32X3));
-    if (!splits_itself && 2.0 * (double)M * (double)N * (double)K >= 1.0e9) {
+    if (!splits_itself && wants_realign(dtype, selector, 2.0 * (double)M * (double)N * (double)K)) {
         RealignJob jobs[2];
         int njobs = 0;
         if (!is_aligned16(A) || lda % vec) {
@@ -1967,7 +2017,7 @@ int jblas_b200_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t ldd, int
     // alignment of device bases is assumed (cudaMalloc gives 256 B); leading dimensions decide the staging path
     const int vec = dtype == JBLAS_B200_DT_F64 ? 2 : 4;
     bool realigned = false;
-    if (2.0 * (double)M * (double)N * (double)K >= 1.0e9 && (lda % vec || ldx % vec)) {  // same rule as gemm_dev
+    if (wants_realign(dtype, selector, 2.0 * (double)M * (double)N * (double)K) && (lda % vec || ldx % vec)) {  // same rule as gemm_dev
         lda = (lda + vec - 1) / vec * vec;
         ldx = (ldx + vec - 1) / vec * vec;
         realigned = true;

@@ -166,15 +166,29 @@ __device__ __forceinline__ void dmma_consume_stage(double (&acc)[Cfg::MI][Cfg::N
     }
 }
 
+// 8-byte cp.async whose completion counts as one arrival on an mbarrier (the RAGGED producers below)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // BATCHED: the tile list runs over `batch` independent products (3-D tensor maps, third coordinate = product; D of product b
 // starts batch_stride_d elements after that of product b-1) -- the fastmul!-class batch for products too big for one warp.
-template <typename Cfg, bool ACC, bool BATCHED = false>
+// RAGGED: operands whose base or leading dimension breaks the 16-byte alignment TMA needs (M = 1023 doubles per column): the
+// whole producer warpgroup stages the tiles with element-wise 8-byte cp.async INTO THE SAME 128B-SWIZZLED LAYOUT the TMA
+// boxes would have, so the consumers, the pipeline and the arithmetic are unchanged and no re-aligned copy of A and X is
+// made (the reference's analogue: the masked row remainder of fastmul!, src/kernels.jl:59-75,101-120).  Out-of-range
+// elements are zero-filled like TMA does.  Tiles are handed out by static stride (the ticket would have to be broadcast).
+template <typename Cfg, bool ACC, bool BATCHED = false, bool RAGGED = false>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS)
 gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
                      double* D, int M, int N, int K, int64_t ldd, int tiles_m, int tiles_n, int group_m,
                      uint64_t l2_policy_a, uint64_t l2_policy_x, int* __restrict__ tile_ctr, const double* Cin, int64_t ldc,
-                     int batch = 1, int64_t batch_stride_d = 0)
+                     int batch = 1, int64_t batch_stride_d = 0, const double* __restrict__ Araw = nullptr, const double* __restrict__ Xraw = nullptr,
+                     int64_t lda = 0, int64_t ldx = 0)
 {
+    static_assert(!(RAGGED && BATCHED) && (!RAGGED || Cfg::MI * Cfg::NI <= 16), "ragged staging: single products, warp tiles that fit 168 registers");
+    constexpr bool REALLOC = Cfg::REALLOC_REGS && !RAGGED;  // the ragged producers do address arithmetic: they keep their registers
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, KSUB = Cfg::KSUB, STAGES = Cfg::STAGES;
     constexpr int MI = Cfg::MI, NI = Cfg::NI;
     extern __shared__ unsigned char smem_raw[];
@@ -188,7 +202,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], RAGGED ? 129 : 1);  // RAGGED: one cp.async-completion arrival per producer thread + one release-arrive
             mbar_init(&empty[s], Cfg::CONSUMER_WARPS);
         }
         mbar_fence_init();
@@ -201,7 +215,79 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
     if (warp >= Cfg::CONSUMER_WARPS) {
         // ===================== producer warpgroup: one thread issues every TMA of the CTA =====================
-        if constexpr (Cfg::REALLOC_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Cfg::PRODUCER_REGS));
+        if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Cfg::PRODUCER_REGS));
+        if constexpr (RAGGED) {
+            const int ptid = tid - Cfg::CONSUMER_WARPS * 32;  // 0..127
+            // Everything that does not change from stage to stage is computed ONCE: the producers share their issue slots with
+            // the DMMA consumers, and recomputing 40 index splits and 64-bit addresses per stage cost 13 % of the kernel.
+            // A sub-tile: BM/16 boxes of 16 rows (k) x 128 B (16 m); element (m, kk): chunk (m%16)/2 ^ (kk & 7), half m & 1
+            // X sub-tile: BN rows (n) x 128 B (16 k);                element (kk, n): chunk kk/2 ^ (n & 7),      half kk & 1
+            constexpr int NA = (BM * 16) / 128, NX = (BN * 16) / 128;
+            uint32_t dstA[NA], dstX[NX];   // shared-memory byte offsets inside a sub-tile
+            int64_t srcA[NA], srcX[NX];    // element offsets from the tile / k origin
+            int mlA[NA], kkA[NA], nlX[NX], kkX[NX];
+#pragma unroll
+            for (int it = 0; it < NA; ++it) {
+                const int idx = ptid + it * 128, ml = idx % BM, kk = idx / BM;
+                mlA[it] = ml; kkA[it] = kk;
+                dstA[it] = (uint32_t)((ml >> 4) * 2048 + kk * 128 + (((((ml & 15) >> 1) ^ (kk & 7))) << 4) + (ml & 1) * 8);
+                srcA[it] = (int64_t)kk * lda + ml;
+            }
+#pragma unroll
+            for (int it = 0; it < NX; ++it) {
+                const int idx = ptid + it * 128, kk = idx & 15, nl = idx >> 4;
+                nlX[it] = nl; kkX[it] = kk;
+                dstX[it] = (uint32_t)(Cfg::A_SUB_BYTES + nl * 128 + ((((kk >> 1) ^ (nl & 7))) << 4) + (kk & 1) * 8);
+                srcX[it] = (int64_t)nl * ldx + kk;
+            }
+            int s = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int tm, tn;
+                raster(tile, tiles_m, tiles_n, group_m, tm, tn);
+                const int m0 = tm * BM, n0 = tn * BN;
+                uint32_t okA = 0, okX = 0;  // row / column of this tile inside the matrix?
+#pragma unroll
+                for (int it = 0; it < NA; ++it) okA |= (uint32_t)(m0 + mlA[it] < M) << it;
+#pragma unroll
+                for (int it = 0; it < NX; ++it) okX |= (uint32_t)(n0 + nlX[it] < N) << it;
+                const double* tileA = Araw + m0;
+                const double* tileX = Xraw + (size_t)n0 * ldx;
+                for (int kt = 0; kt < KT; ++kt) {
+                    mbar_wait(&empty[s], phase ^ 1);
+                    const uint32_t st = smem_u32(tiles) + (uint32_t)s * Cfg::STAGE_BYTES;
+#pragma unroll
+                    for (int sub = 0; sub < KSUB; ++sub) {
+                        const int k0 = kt * BK + sub * 16;
+                        const uint32_t sa = st + sub * Cfg::SUB_BYTES;
+                        const double* pa = tileA + (size_t)k0 * lda;
+                        const double* px = tileX + k0;
+                        const bool kfull = k0 + 16 <= K;  // out-of-range elements are zero-filled, like TMA does
+#pragma unroll
+                        for (int it = 0; it < NA; ++it) {
+                            const bool ok = ((okA >> it) & 1u) && (kfull || k0 + kkA[it] < K);
+                            cp_async8(sa + dstA[it], ok ? pa + srcA[it] : Araw, ok ? 8 : 0);
+                        }
+#pragma unroll
+                        for (int it = 0; it < NX; ++it) {
+                            const bool ok = ((okX >> it) & 1u) && (kfull || k0 + kkX[it] < K);
+                            cp_async8(sa + dstX[it], ok ? px + srcX[it] : Xraw, ok ? 8 : 0);
+                        }
+                    }
+                    cp_async_mbar_arrive_noinc(&full[s]);  // fires when this thread's copies have landed
+                    if (ptid == 0) {
+                        stage_tile[s] = tile;
+                        mbar_arrive(&full[s]);  // release: orders the store above before the consumers' read
+                    }
+                    if (++s == STAGES) { s = 0; phase ^= 1; }
+                }
+            }
+            mbar_wait(&empty[s], phase ^ 1);  // end marker: a stage that carries no data
+            if (ptid == 0) stage_tile[s] = -1;
+            mbar_arrive(&full[s]);
+            if (ptid == 0) mbar_arrive(&full[s]);  // 129 arrivals complete the phase
+            return;
+        }
         if (warp == Cfg::CONSUMER_WARPS && lane == 0) {
             tma_prefetch_desc(&mapA);
             tma_prefetch_desc(&mapX);
@@ -256,7 +342,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
 
     // ===================== consumers: WARPS_M x WARPS_N warps, (MI*8) x (NI*8) each =====================
-    if constexpr (Cfg::REALLOC_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Cfg::CONSUMER_REGS));
+    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Cfg::CONSUMER_REGS));
     const int wm = warp % Cfg::WARPS_M, wn = warp / Cfg::WARPS_M;
     const int g = lane >> 2, t = lane & 3;
     // A fragment: physical row inside a 16-row box for MMA row g of sub-tile 0 (sub-tile 1 adds 4): chunk/half form

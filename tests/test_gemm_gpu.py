@@ -46,6 +46,11 @@ def _dmma_selectors(jb, tma=True):
             if n.startswith("dmma_f64") or (tma and n.startswith("dmma_tma_f64"))]
 
 
+# persistent TMA-layout kernels that also carry element-wise (ragged) producers: misaligned operands are legal for them
+RAGGED_CAPABLE = {"dmma_tma_f64_96x64x32_s4_w8", "dmma_tma_f64_64x64x32_s3_x2", "dmma_tma_f64_128x64x32_s4_w8", "dmma_tma_f64_32x32x64_s3_x2",
+                  "dmma_tma_f64_64x32x32_s4_x2"}
+
+
 def _run_dev(jb, A, X, kernel, accumulate_into=None, ldd=None):
     import torch
 
@@ -173,7 +178,7 @@ def test_dmma_within_reference_tolerance(jb, shape):
     report = {}
     for sel in _dmma_selectors(jb):
         name = jb.kernel_names()[sel - jb.EXPLICIT_BASE]
-        if "tma" in name and (M % 2 or K % 2):  # TMA needs 16-byte aligned leading dimensions; AUTO never picks it here
+        if "tma" in name and (M % 2 or K % 2) and name not in RAGGED_CAPABLE:  # TMA needs 16-byte aligned leading dimensions
             with pytest.raises(jb.JblasB200Error):
                 _run_dev(jb, A, X, sel)
             continue
@@ -207,7 +212,7 @@ def test_dmma_is_bit_identical_to_the_chain_on_b200(jb, shape):
     assert np.signbit(want[0, 0]) and want[0, 0] == 0.0
     for sel in _dmma_selectors(jb):
         name = jb.kernel_names()[sel - jb.EXPLICIT_BASE]
-        if "tma" in name and (M % 2 or K % 2):
+        if "tma" in name and (M % 2 or K % 2) and name not in RAGGED_CAPABLE:
             continue
         got = _run_dev(jb, A, X, sel)
         assert bits_equal(got, want), name
@@ -215,7 +220,7 @@ def test_dmma_is_bit_identical_to_the_chain_on_b200(jb, shape):
     want_acc = oracle.oracle_gemm(A, X, D0.copy(order="F"), accumulate=True)
     for sel in _dmma_selectors(jb):
         name = jb.kernel_names()[sel - jb.EXPLICIT_BASE]
-        if "tma" in name and (M % 2 or K % 2):
+        if "tma" in name and (M % 2 or K % 2) and name not in RAGGED_CAPABLE:
             continue
         assert bits_equal(_run_dev(jb, A, X, sel, accumulate_into=D0), want_acc), name
 
@@ -249,6 +254,35 @@ def test_dmma_tma_kernels_even_strides_accumulate_edges(jb, shape):
         assert ok, worst
         got = _run_dev(jb, A, X, sel, accumulate_into=D0)
         assert np.abs(got - want_acc).max() <= 2 * K * 2.0 ** -52 * (np.abs(Ad) @ np.abs(Xd) + np.abs(D0)).max()
+
+
+@pytest.mark.parametrize("shape", [(1023, 4097, 777), (129, 37, 255), (333, 64, 191), (2050, 129, 1031), (1, 3, 1)], ids=str)
+def test_ragged_producers_bit_identical(jb, shape):
+    """The element-wise (RAGGED) producers of the persistent kernels: odd row counts and leading dimensions, an odd base
+    offset (a sub-matrix view starting at row 1), ragged M / N / K edges, overwrite and accumulate -- every bit of the chain
+    (they write the same swizzled layout the TMA boxes would, so the consumers are the TMA kernels' own)."""
+    import torch
+    from jblas.jl_b200 import api
+
+    M, K, N = shape
+    A, X = randn_f((M, K), ld=M + 3), randn_f((K, N), seed=SEED_X, ld=K + 1 + (K % 2))  # lda odd or even+odd mix, ldx odd
+    Ad, Xd = np.asfortranarray(A), np.asfortranarray(X)
+    want = oracle.oracle_gemm(Ad, Xd)
+    D0 = randn_f((M, N), seed=5)
+    want_acc = oracle.oracle_gemm(Ad, Xd, D0.copy(order="F"), accumulate=True)
+    for i, name in enumerate(jb.kernel_names()):
+        if name not in RAGGED_CAPABLE:
+            continue
+        sel = jb.EXPLICIT_BASE + i
+        assert bits_equal(_run_dev(jb, A, X, sel, ldd=M + 1), want), name
+        assert bits_equal(_run_dev(jb, A, X, sel, accumulate_into=D0), want_acc), name
+    if M > 2:  # a view that starts one row down: the BASE is off the 16-byte grid even where the leading dimension is even
+        Ap = randn_f((M + 1, K), ld=M + 3 + ((M + 3) % 2))
+        dA = to_dev(Ap)[1:, :]
+        dX, dD = to_dev(X), to_dev(nan_f((M, N)))
+        api._gemm(dD, dA, dX, False, jb.F64_AUTO)
+        torch.cuda.synchronize()
+        assert bits_equal(to_host(dD), oracle.oracle_gemm(np.asfortranarray(Ap[1:, :]), Xd))
 
 
 def test_dmma_tma_dynamic_tile_scheduler_many_tiles_repeated_and_concurrent(jb):
@@ -393,7 +427,8 @@ def test_ragged_operands_are_realigned_in_one_pass(jb, dt):
     got = _run_dev(jb, A, X, jb.F64_SIMT if dt == np.float64 else jb.F32_EXACT)
     assert bits_equal(got, want)
     if dt == np.float64:
-        assert "re-aligning" in jb.plan(M, K, N, lda=M + 2, ldx=K + 6)["staging"]
+        assert "ragged producer" in jb.plan(M, K, N, lda=M + 2, ldx=K + 6)["staging"]  # f64 tensor path: staged inside the kernel
+        assert "re-aligning" in jb.plan(M, K, N, lda=M + 2, ldx=K + 6, kernel=jb.F64_SIMT)["staging"]
         ok, worst = oracle.error_bound_ok(_run_dev(jb, A, X, jb.F64_AUTO), want, np.asfortranarray(A), np.asfortranarray(X))
         assert ok, worst
 

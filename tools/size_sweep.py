@@ -32,7 +32,7 @@ for dtype in dtypes:
         if ALL and M * N * K <= 2 ** 33:
             per = {}
             for i, n in enumerate(names):
-                fam = ("dmma_tma_f64" in n) if dtype == "float64" else ("simt_f32x2" in n)
+                fam = ("dmma_tma_f64" in n) if dtype == "float64" else ("simt_f32x2" in n or "simt_f32_tma" in n)
                 if not fam:
                     continue
                 try:
