@@ -31,6 +31,7 @@ SEED_X = SEED_A + 1
 METRIC = "GEMM TFLOP/s (FP64, FP32) and % of roofline at 1/2/4/8 B200 vs CPU jBLAS"
 FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
 FP32_NOMINAL_TFLOPS = 74.4
+TF32X3_NOMINAL_TFLOPS = 1125.0 / 3  # dense TF32 tensor peak (half the 2.25 PFLOP/s bf16 figure) / 3 MMAs per product
 
 WORKLOADS = {
     # name: (dtype, M, N, K, description)
@@ -376,6 +377,8 @@ def time_other_config(jb, name, kernel=None, extra_rel=0.0):
     A, X, D = bufs[0]
     par = parity_sample(D, A, X, extra_rel=extra_rel)
     nominal = FP64_NOMINAL_TFLOPS if dtype == "float64" else FP32_NOMINAL_TFLOPS
+    if kernel is not None and dtype == "float32" and kernel == jb.F32_3XTF32:
+        nominal = TF32X3_NOMINAL_TFLOPS  # three TF32 MMAs per credited FMA
     out = {"config": name, "workload": desc, "kernel": jb.plan(M, K, N, dtype, kernel=kernel)["kernel"], "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12,
            "frac_of_nominal": flops / (ms * 1e-3) / 1e12 / nominal, "nominal_peak": nominal, "algorithmic_gbs": bytes_ / (ms * 1e-3) / 1e9,
            "reps": reps, "l2": f"{sets} rotating operand sets ({sets * bytes_ / 1e6:.0f} MB)" if sets > 1 else f"operands {bytes_ / 1e6:.0f} MB > L2",

@@ -398,11 +398,13 @@ def plan(M: int, K: int, N: int, dtype="float64", kernel: int | None = None, ldd
     L = _lib.lib()
     check(L.jblas_b200_plan(dt, M, K, N, ldd or M, lda or M, ldx or K, kernel, out))
     name = L.jblas_b200_kernel_name(int(out[0])).decode()
-    if "tma" in name and out[9] == 0:  # misaligned operands on a persistent TMA-layout kernel: its ragged producers
+    if name.startswith("tf32x3"):
+        staging = "hi/lo TF32 split pre-pass into K-major scratch, then TMA cp.async.bulk.tensor, 128B swizzle"
+    elif "tma" in name and out[9] == 0:  # misaligned operands on a persistent TMA-layout kernel: its ragged producers
         staging = "cp.async element-wise into the 128B-swizzled TMA layout (ragged producer warpgroup, no scratch copy)"
     else:
         staging = "TMA cp.async.bulk.tensor, 128B swizzle" if "tma" in name else ("cp.async 16B" if out[9] else "cp.async element-wise")
-    if out[9] == 2:
+    if out[9] == 2 and not name.startswith("tf32x3"):
         staging += " (after re-aligning the ragged operand into scratch)"
     return {
         "kernel": name,

@@ -164,6 +164,7 @@ struct KernelInfo {
     cudaError_t (*set_attr)();
     int (*query_occ)();  // non-persistent kernels: CTAs of the aligned variant the hardware keeps resident per SM
     bool has_ragged = false;  // needs_aligned kernels only: launch[0][*] is an element-wise staging variant, not an error
+    int cluster = 1;          // CTAs (SMs) that work on ONE bm x bn tile together (2: tcgen05 cta_group::2 pair)
 };
 template <typename K>
 static int occupancy_of(K kernel, int threads, size_t smem)
@@ -378,10 +379,11 @@ static int launch_needs_alignment(void*, const void*, const void*, int, int, int
 {
     return fail(JBLAS_B200_EUNSUPPORTED, "this kernel needs 16-byte aligned A/X bases and even leading dimensions (TMA)");
 }
-// 3xTF32: split A and X into (hi, lo) TF32 parts in stream-ordered scratch, then the tcgen05/TMEM kernel.
-template <typename Cfg, bool ACC>
-static int launch_tf32x3(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
-                         int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
+// 3xTF32: split A and X into (hi, lo) TF32 parts in stream-ordered scratch, then the tcgen05/TMEM kernel (PAIR: the
+// cta_group::2 kernel, two CTAs per 256 x 256 tile).
+template <typename Cfg, bool ACC, bool PAIR>
+static int launch_tf32x3_any(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                             int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
 {
     const int64_t ldA2 = (K + 3) / 4 * 4, ldX2 = (K + 3) / 4 * 4;  // A is stored transposed: K contiguous, M columns
     float* parts = nullptr;  // [A^T_hi | A^T_lo | X_hi | X_lo]
@@ -398,19 +400,47 @@ static int launch_tf32x3(void* D, const void* A, const void* X, int M, int N, in
     }
     split_tf32_kernel<<<dim3((unsigned)((K + 255) / 256), (unsigned)(N < 65535 ? N : 65535)), 256, 0, s>>>((const float*)X, ldx, K, N, Xhi, Xlo, ldX2);
     g_launches += 2;
+    constexpr uint32_t box_m = PAIR ? 128 : Cfg::BM, box_n = PAIR ? 128 : Cfg::BN;  // a pair's CTA stages half of the tile's rows and columns
     CUtensorMap mAh, mAl, mXh, mXl;
-    int rc = make_tmap_2d(&mAh, Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)M, (uint64_t)ldA2, 32, Cfg::BM);
-    if (!rc) rc = make_tmap_2d(&mAl, Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)M, (uint64_t)ldA2, 32, Cfg::BM);
-    if (!rc) rc = make_tmap_2d(&mXh, Xhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)N, (uint64_t)ldX2, 32, Cfg::BN);
-    if (!rc) rc = make_tmap_2d(&mXl, Xlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)N, (uint64_t)ldX2, 32, Cfg::BN);
+    int rc = make_tmap_2d(&mAh, Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)M, (uint64_t)ldA2, 32, box_m);
+    if (!rc) rc = make_tmap_2d(&mAl, Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)M, (uint64_t)ldA2, 32, box_m);
+    if (!rc) rc = make_tmap_2d(&mXh, Xhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)N, (uint64_t)ldX2, 32, box_n);
+    if (!rc) rc = make_tmap_2d(&mXl, Xlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)K, (uint64_t)N, (uint64_t)ldX2, 32, box_n);
     if (!rc) {
-        int grid = tiles_m * tiles_n;
-        if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
-        gemm_tf32x3_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mAh, mAl, mXh, mXl, (float*)D, M, N, K, ldd, tiles_m, tiles_n, group_m,
-                                                                           (const float*)Cin, ldc);
+        if constexpr (PAIR) {
+            int grid = 2 * tiles_m * tiles_n;  // one cluster of two CTAs per tile, persistent over the tile list
+            const int most = g_ctx.num_sms & ~1;
+            if (grid > most) grid = most;
+            gemm_tf32x3_pair_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mAh, mAl, mXh, mXl, (float*)D, M, N, K, ldd, tiles_m, tiles_n, group_m,
+                                                                                     (const float*)Cin, ldc);
+        } else {
+            int grid = tiles_m * tiles_n;
+            if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
+            gemm_tf32x3_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mAh, mAl, mXh, mXl, (float*)D, M, N, K, ldd, tiles_m, tiles_n, group_m,
+                                                                               (const float*)Cin, ldc);
+        }
     }
     cudaFreeAsync(parts, s);
     return rc;
+}
+template <typename Cfg, bool ACC>
+static int launch_tf32x3(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                         int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
+{
+    return launch_tf32x3_any<Cfg, ACC, false>(D, A, X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m, s, Cin, ldc);
+}
+template <typename Cfg, bool ACC>
+static int launch_tf32x3_pair(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
+                              int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
+{
+    return launch_tf32x3_any<Cfg, ACC, true>(D, A, X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m, s, Cin, ldc);
+}
+template <typename Cfg>
+static cudaError_t attr_tf32x3_pair()
+{
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gemm_tf32x3_pair_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
 }
 template <typename Cfg>
 static cudaError_t attr_tf32x3()
@@ -460,6 +490,13 @@ static cudaError_t attr_dmma_tma()
             false, true, 1,                                                                                        \
             {{launch_tf32x3<CFG, false>, launch_tf32x3<CFG, true>}, {launch_tf32x3<CFG, false>, launch_tf32x3<CFG, true>}}, \
             attr_tf32x3<CFG>, nullptr                                                                              \
+    }
+#define TF32X3_PAIR_ENTRY(NAME, CFG, EFF)                                                                          \
+    {                                                                                                              \
+        NAME, JBLAS_B200_DT_F32, FAM_TF32X3, CFG::BM, CFG::BN, CFG::BK, CFG::STAGES, CFG::THREADS, CFG::SMEM, EFF, \
+            false, true, 1,                                                                                        \
+            {{launch_tf32x3_pair<CFG, false>, launch_tf32x3_pair<CFG, true>}, {launch_tf32x3_pair<CFG, false>, launch_tf32x3_pair<CFG, true>}}, \
+            attr_tf32x3_pair<CFG>, nullptr, false, 2                                                               \
     }
 #define DMMA_TMA_ENTRY(NAME, CFG, EFF)                                                                             \
     {                                                                                                              \
@@ -515,6 +552,7 @@ using F2_32x32_w2 = F32x2Cfg<1, 2, 1, 4, 16, 4, 8>;  // 2 warps of 32x16
 using F32T_s4 = F32TmaCfg<4>;          // 128 x 256 x 32, 4 stages of 48 KiB
 using X3_128x256 = Tf32x3Cfg<256, 2>;  // 2 stages of 96 KiB, two 256-column TMEM accumulators
 using X3_128x128 = Tf32x3Cfg<128, 3>;  // 3 stages of 64 KiB
+using X3_PAIR = Tf32x3PairCfg<3>;      // cta_group::2: 256 x 256 per CTA pair, 3 stages of 64 KiB per CTA
 
 // NOTE: indices are part of the tuning interface (selector 100+i); append, do not reorder.
 static const KernelInfo g_kernels[] = {
@@ -547,6 +585,7 @@ static const KernelInfo g_kernels[] = {
     /* 26 */ SIMT_F32X2_ENTRY("simt_f32x2_64x32x16_w4", F2_64x32_w4, 1.00f),
     /* 27 */ SIMT_F32X2_ENTRY("simt_f32x2_32x32x16_w2", F2_32x32_w2, 1.00f),
     /* 28 */ F32_TMA_ENTRY("simt_f32_tma_ffma2_128x256x32_s4", F32T_s4, 1.40f),
+    /* 29 */ TF32X3_PAIR_ENTRY("tf32x3_tcgen05_2cta_f32_256x256x32_s3", X3_PAIR, 1.11f),  // 8192^3: 270.8 vs 243.7 TFLOP/s, 16384^3: 239 vs 214 (same box, incl. the split)
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
 static int g_occ[NUM_KERNELS] = {0};  // measured residency (filled at init); 0 = unknown, the planner uses ctas_per_sm
@@ -603,13 +642,14 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
         if (explicit_idx >= 0 ? (i != explicit_idx) : (k.dtype != dtype || k.family != family)) continue;
         if (explicit_idx < 0 && k.needs_aligned && !out->aligned && !k.has_ragged) continue;
         int64_t tiles = ((M + k.bm - 1) / k.bm) * ((N + k.bn - 1) / k.bn);
-        double per_tile = (double)k.bm * k.bn;
+        double per_tile = (double)k.bm * k.bn / k.cluster;  // a pair works through its tile in half the time
         // rounds of resident CTAs; CTAs that share an SM (ctas_per_sm > 1) also share its pipes, so a round of c
         // co-resident CTAs costs c tile-times once more than one of them actually lands on an SM
-        const int64_t resident = (int64_t)num_sms * k.ctas_per_sm;
+        const int64_t units = num_sms / k.cluster;  // SMs, or SM pairs
+        const int64_t resident = units * k.ctas_per_sm;
         const int64_t rounds = (tiles + resident - 1) / resident;
         const int64_t last = tiles - (rounds - 1) * resident;                          // CTAs in the last round
-        const int64_t last_share = (last + num_sms - 1) / num_sms;                     // how many of them share an SM
+        const int64_t last_share = (last + units - 1) / units;                         // how many of them share an SM
         // a CTA built to share its SM but left alone on it runs at ~0.8 of the shared rate (nothing overlaps its
         // pipeline fill and epilogue): measured, profiles/r1_size_sweep_per_kernel.json
         double waves = (double)((rounds - 1) * k.ctas_per_sm) + (last_share < k.ctas_per_sm ? 1.25 * last_share : (double)last_share);
@@ -2025,8 +2065,8 @@ int jblas_b200_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t ldd, int
     if (int rc = make_plan(dtype, M, K, N, lda, ldx, nullptr, nullptr, selector, &p)) return rc;
     const KernelInfo& k = g_kernels[p.kidx];
     out[0] = p.kidx; out[1] = k.bm; out[2] = k.bn; out[3] = k.bk; out[4] = k.stages; out[5] = k.threads;
-    out[6] = (int64_t)p.tiles_m * p.tiles_n;
-    const int64_t resident = (int64_t)(g_ctx.num_sms > 0 ? g_ctx.num_sms : 148) * k.ctas_per_sm;
+    out[6] = (int64_t)p.tiles_m * p.tiles_n * k.cluster;  // CTAs: a cta_group::2 tile takes a pair
+    const int64_t resident = (int64_t)(g_ctx.num_sms > 0 ? g_ctx.num_sms : 148) / k.cluster * k.cluster * k.ctas_per_sm;
     if (k.persistent && out[6] > resident) out[6] = resident;
     out[7] = p.group_m; out[8] = (int64_t)k.smem; out[9] = realigned ? 2 : (p.aligned ? 1 : 0);
     return 0;

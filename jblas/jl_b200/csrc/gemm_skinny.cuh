@@ -27,8 +27,16 @@
 //     step (ptxas otherwise chains the steps of one accumulator back to back and stalls on the DMMA latency: measured 46 %
 //     tensor pipe with register-resident A).
 //   * accumulators start at -0.0 (or C): ascending k, 4 per DMMA -> bit-identical to the reference chain on B200.
-// Blocks are dealt round-robin over ALL warps of the grid with the CTA index fastest, so the blocks in flight at any moment
-// are neighbours in memory and every SM sub-partition gets the same count (+-1).
+// Work distribution.  Blocks are dealt round-robin over ALL warps of the grid with the CTA index fastest, so the blocks in
+// flight at any moment are neighbours in memory.  65536 rows are 4096 blocks for 1184 warps = 3.46 each: dealing whole blocks
+// costs a fourth round on every SM (measured: 26.6 us against 4.5 us of start-up + 3.46 x 4.8 us).  So only the
+// floor(blocks / warps) full rounds are dealt as whole blocks; the REMAINDER is dealt as half blocks (16 rows x half of the
+// column tiles: the A box is fetched twice, from L2 the second time), one or two per warp.  The second warp of every SM
+// sub-partition (warps 4..7 of 8) takes its half items FIRST, the first warp takes them LAST: the two warps that share a DMMA
+// pipe then reach their epilogues half a block apart instead of together (stores + accumulator re-initialisation + the wait
+// for the next box of one warp hide behind the other warp's MMAs).
+// Start-up: every warp requests only its FIRST box before X has landed and the second one after -- all first boxes are then
+// served ahead of all second boxes by HBM (19 MB requested at t = 0 take 3 us to arrive, in no particular order).
 #pragma once
 #include <cuda.h>
 
@@ -47,14 +55,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-template <int NI_, int WARPS_, int KC_ = 64, int EXP_ = 0>
+template <int NI_, int WARPS_, int KC_ = 64, int FLAGS_ = 3>
 struct SkinnyCfg {
-    static constexpr bool TWO_ACC = false;
-    static constexpr int EXP = EXP_;  // development experiments (tools/skinny_probe): 1 = no stores, 2 = every chunk has KC/4 steps (compile-time trip count)
+    static constexpr int FLAGS = FLAGS_;  // bit 0: stagger the half items (above); bit 1: second box requested after X has landed
     static constexpr int NI = NI_, WARPS = WARPS_, THREADS = WARPS_ * 32, BN = NI_ * 8;
     static constexpr int KC = KC_;                    // k chunk of one TMA box (multiple of 8)
     static constexpr int BOX_BYTES = 16 * KC * 8;     // 16 rows x KC columns of doubles
     static constexpr int NBUF = 2;
+    static_assert(NI_ % 2 == 0, "half items take NI / 2 column tiles");
     static_assert(KC_ % 8 == 0 && BOX_BYTES % 1024 == 0, "a box is a whole number of swizzle atoms");
     // X lives in shared memory FRAGMENT-MAJOR, sX[s][n][t]: the 32 doubles lane (g, t) = X[4s + t][8 ni + g] of k-step s, column
     // tile ni are contiguous in lane order, so every fragment load is base + lane*8 + immediate (conflict-free)
@@ -62,12 +70,17 @@ struct SkinnyCfg {
     static size_t smem(int K) { return (size_t)WARPS * NBUF * BOX_BYTES + x_bytes(K) + (WARPS * NBUF + 1) * sizeof(uint64_t) + 1024; }
 };
 
+template <int V>
+struct IntC {
+    static constexpr int value = V;
+};
+
 template <typename Cfg, bool ACC>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX, double* __restrict__ D, int M, int N, int K,
                        int64_t ldd, const double* __restrict__ Cin, int64_t ldc, unsigned long long* trace = nullptr)
 {
-    // development aid (tools/skinny_probe): per-warp %globaltimer stamps -- [0] entry, [1] X staged, [2] first box landed, [3+i] block i stored
+    // development aid (tools/skinny_probe): per-warp %globaltimer stamps -- [0] entry, [1] X staged, [2] first box landed, [3+i] item i stored
     auto stamp = [&](int slot) {
         if (trace && (threadIdx.x & 31) == 0 && slot < 12) {
             unsigned long long tns;
@@ -88,8 +101,24 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     uint64_t* full = bars + warp * NBUF;
 
     const int nblocks = (M + 15) >> 4, nchunks = (K + KC - 1) / KC;
-    const int total_warps = gridDim.x * Cfg::WARPS;
-    const int first = warp * gridDim.x + blockIdx.x;  // CTA index fastest: every SM sub-partition gets the same number of blocks (+-1)
+    const int W = gridDim.x * Cfg::WARPS;
+    const int wid = warp * gridDim.x + blockIdx.x;  // CTA index fastest: every SM sub-partition gets the same number of items (+-1)
+    // items of this warp: `rounds` whole blocks wid + i W, then the remainder of the block list as half blocks h = wid (+ W)
+    const int rounds = nblocks / W, nhalves = 2 * (nblocks - rounds * W);
+    const int nhalf = (wid < nhalves ? 1 : 0) + (wid + W < nhalves ? 1 : 0);
+    const int nitems = rounds + nhalf;
+    const bool halves_first = (Cfg::FLAGS & 1) && ((warp >> 2) & 1) && nhalf > 0;
+    auto item = [&](int j, int& blk, int& half) {  // half: -1 = whole block, else which half of the column tiles
+        const int jf = halves_first ? j - nhalf : j, jh = halves_first ? j : j - rounds;
+        if (jf >= 0 && jf < rounds) {
+            blk = wid + jf * W;
+            half = -1;
+        } else {
+            const int h = wid + jh * W;
+            blk = rounds * W + (h >> 1);
+            half = h & 1;
+        }
+    };
 
     // ---- X first: ONE 3-D TMA box (t, n, s) -> sX[s][n][t], which is fragment-major: the 32 lane values X[4s + t][8 ni + g] of
     //      a fragment are contiguous in lane order (conflict-free, address = base + immediate).  Columns n >= N are zero-filled
@@ -97,6 +126,8 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     //      the start-up burst of A requests. ----
     uint64_t* xbar = bars + Cfg::WARPS * NBUF;
     if (tid == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapA);
         mbar_init(xbar, 1);
         mbar_fence_init();
         mbar_expect_tx(xbar, (uint32_t)(ksteps * Cfg::BN * 32));
@@ -108,61 +139,59 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         mbar_fence_init();
     }
     __syncwarp();
-    // item i of this warp = (block first + (i / nchunks) * total_warps, chunk i % nchunks)
-    auto issue = [&](int blk, int chunk, int buf) {
-        if (lane == 0) {
+    int ij = 0, ic = 0;  // next box to REQUEST: item ij, chunk ic
+    auto request = [&](int buf) {
+        if (ij < nitems && lane == 0) {
+            int blk, half;
+            item(ij, blk, half);
             mbar_expect_tx(&full[buf], Cfg::BOX_BYTES);
-            tma_load_4d(myA + buf * Cfg::BOX_BYTES, &mapA, &full[buf], blk * 16, 0, 0, chunk * (KC / 8));
+            tma_load_4d(myA + buf * Cfg::BOX_BYTES, &mapA, &full[buf], blk * 16, 0, 0, ic * (KC / 8));
         }
+        if (++ic == nchunks) { ic = 0; ++ij; }
     };
-    int iblk = first, ichunk = 0;  // next item to ISSUE
-    auto advance = [&](int& blk, int& chunk) {
-        if (++chunk == nchunks) { chunk = 0; blk += total_warps; }
-    };
-#pragma unroll
-    for (int b = 0; b < NBUF; ++b) {
-        if (iblk < nblocks) issue(iblk, ichunk, b);
-        advance(iblk, ichunk);
-    }
+    request(0);
+    if (!(Cfg::FLAGS & 2)) request(1);
     __syncthreads();  // xbar is initialised for everybody
     mbar_wait(xbar, 0);
+    if (Cfg::FLAGS & 2) request(1);
     stamp(1);
 
     const uint32_t sB = smem_u32(sX + lane);                    // + ((k0/4 + s) * NI + ni) * 256
     // rows (2g, 2g+1) of column k = 4s + t of a box: row R = 8 (s >> 1) + 2t + (s & 1), chunk g ^ (R & 7)
     const uint32_t sA0 = smem_u32(myA);
     const uint32_t offA[2] = {(uint32_t)((2 * t) * 128 + ((g ^ (2 * t)) << 4)), (uint32_t)((2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4))};
-    // Fast paths (warp-uniform): a block whose 16 rows all exist, all BN columns exist and whose D (and C) columns are 16-byte
-    // aligned moves through pointer increments only -- the general path costs ~430 instructions per block, and with every warp
-    // of an SM sub-partition reaching its epilogue at the same moment that time is NOT hidden (measured: 26 % of the kernel).
-    const bool vec_ok = N == Cfg::BN && (ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 &&
+    // Fast path (warp-uniform): a block whose 16 rows all exist and whose D (and C) columns are 16-byte aligned moves through
+    // 16-byte accesses off one base pointer -- the element-wise path costs ~430 instructions per block.
+    const bool vec_ok = (ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 &&
                         (!ACC || ((ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(Cin) & 15) == 0));
-    const int64_t col0 = 2 * t;  // this lane's first column; the others are col0 + 8 ni + c
 
-    int blk = first, buf = 0, done = 0;
+    int buf = 0, done = 0;
     uint32_t phase = 0;
-    // One block of D: all k chunks, then the stores.  Called alternately with TWO accumulator sets: the stores of a block read
-    // their registers asynchronously, and re-initialising the same registers for the next block would wait for them.
-    auto process = [&](double (&acc)[2][NI][2]) {
+    // One item: NIC column tiles starting at tile NI0 of block blk -- all k chunks, then the stores.
+    auto process = [&](auto ni0_c, auto nic_c, int blk) {
+        constexpr int NI0 = decltype(ni0_c)::value, NIC = decltype(nic_c)::value;
+        double acc[2][NIC][2];
         const int m = blk * 16 + 2 * g;
+        const int ncol0 = NI0 * 8 + 2 * t;  // this lane's first column; the others are ncol0 + 8 ni + c
         const bool fast = vec_ok && blk * 16 + 16 <= M;
         if constexpr (ACC) {
             if (fast) {
-                const double* p = Cin + col0 * ldc + m;
+                const double* p = Cin + (int64_t)ncol0 * ldc + m;
 #pragma unroll
-                for (int ni = 0; ni < NI; ++ni)
+                for (int ni = 0; ni < NIC; ++ni)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        const double2 v = *reinterpret_cast<const double2*>(p + (int64_t)(ni * 8 + c) * ldc);
+                        double2 v = make_double2(0.0, 0.0);
+                        if (ncol0 + ni * 8 + c < N) v = *reinterpret_cast<const double2*>(p + (int64_t)(ni * 8 + c) * ldc);
                         acc[0][ni][c] = v.x;
                         acc[1][ni][c] = v.y;
                     }
             } else {
 #pragma unroll
-                for (int ni = 0; ni < NI; ++ni)
+                for (int ni = 0; ni < NIC; ++ni)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        const int n = ni * 8 + 2 * t + c;
+                        const int n = ncol0 + ni * 8 + c;
                         double2 v = make_double2(0.0, 0.0);
                         if (n < N) {
                             const double* p = Cin + (size_t)n * ldc + m;
@@ -175,7 +204,7 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             }
         } else {
 #pragma unroll
-            for (int ni = 0; ni < NI; ++ni)
+            for (int ni = 0; ni < NIC; ++ni)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) acc[0][ni][c] = acc[1][ni][c] = -0.0;
         }
@@ -183,65 +212,47 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             mbar_wait(&full[buf], phase);
             if (done == 0 && chunk == 0) stamp(2);
             const int s0 = chunk * (KC / 4);
-            const int steps = (Cfg::EXP & 2) ? KC / 4 : min(ksteps - s0, KC / 4);  // even: K % 8 == 0
-            const uint32_t pa = sA0 + buf * Cfg::BOX_BYTES, pb = sB + s0 * NI * 256;
+            const int steps = min(ksteps - s0, KC / 4);  // even: K % 8 == 0
+            const uint32_t pa = sA0 + buf * Cfg::BOX_BYTES, pb = sB + (s0 * NI + NI0) * 256;
             double2 a[2];
-            double b[2][NI];
+            double b[2][NIC];
             auto load = [&](int s, int which) {
                 asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(a[which].x), "=d"(a[which].y) : "r"(pa + offA[which] + (s >> 1) * 1024));
 #pragma unroll
-                for (int ni = 0; ni < NI; ++ni) b[which][ni] = lds_f64(pb + (s * NI + ni) * 256);
+                for (int ni = 0; ni < NIC; ++ni) b[which][ni] = lds_f64(pb + (s * NI + ni) * 256);
             };
             auto mma = [&](int which) {
 #pragma unroll
-                for (int ni = 0; ni < NI; ++ni) {
+                for (int ni = 0; ni < NIC; ++ni) {
                     dmma884(acc[0][ni][0], acc[0][ni][1], a[which].x, b[which][ni]);
                     dmma884(acc[1][ni][0], acc[1][ni][1], a[which].y, b[which][ni]);
                 }
             };
             load(0, 0);
-            if constexpr (Cfg::EXP & 2) {
-#pragma unroll
-                for (int s = 0; s < KC / 4; s += 2) {
-                    load(s + 1, 1);
-                    mma(0);
-                    if (s + 2 < KC / 4) load(s + 2, 0);
-                    mma(1);
-                }
-            } else {
 #pragma unroll 2
-                for (int s = 0; s < steps; s += 2) {
-                    load(s + 1, 1);
-                    mma(0);
-                    if (s + 2 < steps) load(s + 2, 0);
-                    mma(1);
-                }
+            for (int s = 0; s < steps; s += 2) {
+                load(s + 1, 1);
+                mma(0);
+                if (s + 2 < steps) load(s + 2, 0);
+                mma(1);
             }
             __syncwarp();  // every lane has read the box: it may be overwritten
-            if (iblk < nblocks) issue(iblk, ichunk, buf);
-            advance(iblk, ichunk);
+            request(buf);
             if (++buf == NBUF) { buf = 0; phase ^= 1; }
         }
-        if constexpr (Cfg::EXP & 1) {
-            double sum = 0;
+        if (fast) {
+            double* p = D + (int64_t)ncol0 * ldd + m;
 #pragma unroll
-            for (int ni = 0; ni < NI; ++ni)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) sum += acc[0][ni][c] * acc[1][ni][c];
-            if (sum == 1.2345678) D[m] = sum;
-        } else if (fast) {
-            double* p = D + col0 * ldd + m;
-#pragma unroll
-            for (int ni = 0; ni < NI; ++ni)
+            for (int ni = 0; ni < NIC; ++ni)
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
-                    *reinterpret_cast<double2*>(p + (int64_t)(ni * 8 + c) * ldd) = make_double2(acc[0][ni][c], acc[1][ni][c]);
+                    if (ncol0 + ni * 8 + c < N) *reinterpret_cast<double2*>(p + (int64_t)(ni * 8 + c) * ldd) = make_double2(acc[0][ni][c], acc[1][ni][c]);
         } else {
 #pragma unroll
-            for (int ni = 0; ni < NI; ++ni)
+            for (int ni = 0; ni < NIC; ++ni)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const int n = ni * 8 + 2 * t + c;
+                    const int n = ncol0 + ni * 8 + c;
                     if (n >= N) continue;
                     double* p = D + (size_t)n * ldd + m;
                     if (m < M) p[0] = acc[0][ni][c];
@@ -250,18 +261,13 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         }
         stamp(3 + done);
         ++done;
-        blk += total_warps;
     };
-    if constexpr (Cfg::TWO_ACC) {
-        double accA[2][NI][2], accB[2][NI][2];
-        while (blk < nblocks) {
-            process(accA);
-            if (blk >= nblocks) break;
-            process(accB);
-        }
-    } else {
-        double acc[2][NI][2];
-        while (blk < nblocks) process(acc);
+    for (int j = 0; j < nitems; ++j) {
+        int blk, half;
+        item(j, blk, half);
+        if (half < 0) process(IntC<0>{}, IntC<NI>{}, blk);
+        else if (half == 0) process(IntC<0>{}, IntC<NI / 2>{}, blk);
+        else process(IntC<NI / 2>{}, IntC<NI / 2>{}, blk);
     }
 }
 

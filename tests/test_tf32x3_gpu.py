@@ -72,6 +72,28 @@ def test_tf32x3_strided_and_accumulate(jb):
     assert (np.abs(got.astype(np.float64) - want_acc) <= bound).all()
 
 
+@pytest.mark.parametrize("shape", [(256, 32, 256), (512, 96, 768), (300, 270, 100), (129, 40, 513), (1024, 4096, 1280)], ids=lambda s: "x".join(map(str, s)))
+def test_tf32x3_cta_pair_kernel_equals_single_cta_kernel(jb, shape):
+    """cta_group::2 (two CTAs per 256 x 256 tile, X shared across the pair) issues the same MMA sequence per element as the
+    single-CTA kernel: lo*hi, hi*lo, hi*hi per 8 k, ascending k, one FP32 TMEM accumulator -- so every bit agrees, for
+    overwrite and accumulate, including tiles that hang over the matrix edge in M (second CTA of a pair idle) and N."""
+    M, K, N = shape
+    names = jb.kernel_names()
+    one = jb.EXPLICIT_BASE + names.index("tf32x3_tcgen05_f32_128x256x32_s2")
+    pair = jb.EXPLICIT_BASE + names.index("tf32x3_tcgen05_2cta_f32_256x256x32_s3")
+    A, X = randn_f((M, K), np.float32, SEED_A), randn_f((K, N), np.float32, SEED_X)
+    a, b = _run(jb, A, X, one), _run(jb, A, X, pair)
+    assert not np.isnan(b).any(), "unwritten element"
+    assert a.tobytes() == b.tobytes()
+    D0 = randn_f((M, N), np.float32, 5)
+    assert _run(jb, A, X, one, acc_into=D0).tobytes() == _run(jb, A, X, pair, acc_into=D0).tobytes()
+
+
+def test_tf32x3_auto_picks_the_pair_kernel_for_big_products(jb):
+    assert jb.plan(16384, 16384, 16384, "float32", kernel=jb.F32_3XTF32)["kernel"] == "tf32x3_tcgen05_2cta_f32_256x256x32_s3"
+    assert jb.plan(128, 512, 4096, "float32", kernel=jb.F32_3XTF32)["kernel"].startswith("tf32x3_tcgen05_f32_128x")  # one tile row: no pair
+
+
 def test_tf32x3_host_pointer_entry(jb):
     M, K, N = 515, 260, 333
     A, X = randn_f((M, K), np.float32), randn_f((K, N), np.float32, SEED_X)

@@ -232,13 +232,13 @@ int main(int argc, char** argv)
         return 0;
     }
     printf("M %d N %d K %d, %d SMs, %d rotating sets (%.0f MB)\n", M, N, K, sms, R, R * ((double)M * K + (double)M * N) * 8 / 1e6);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64>>("w8 kc64", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 1>>("w8 kc64 nostore", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 2>>("w8 kc64 static", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 3>>("w8 kc64 static nostore", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 16, 16, 2>>("w16 kc16 static", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 16, 16>>("w16 kc16", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 4, 64, 2>>("w4 kc64 static", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 4, 64, 3>>("w4 kc64 static nostore", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 0>>("w8 kc64 plain halves", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 1>>("w8 kc64 stagger", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 2>>("w8 kc64 late 2nd box", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 3>>("w8 kc64 stagger+late", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 32, 3>>("w8 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 16, 16, 3>>("w16 kc16 stagger+late", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 16, 32, 3>>("w16 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 12, 32, 3>>("w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     return 0;
 }
