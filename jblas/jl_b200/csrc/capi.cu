@@ -24,6 +24,7 @@
 #include "gemm_f32_tma.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_simt_f32x2.cuh"
+#include "gemm_skinny.cuh"
 #include "gemm_tf32x3.cuh"
 
 using namespace jb;
@@ -374,6 +375,82 @@ static cudaError_t attr_dmma_tma_ragged()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     return e;
 }
+// General tiled tensor map (rank 3 or 4, Float64) with a small per-thread cache, as make_tmap_2d.
+static int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstride_bytes, const cuuint32_t* box,
+                        CUtensorMapSwizzle swizzle)
+{
+    struct Entry { const void* base; cuuint64_t gdim[4], gstr[3]; cuuint32_t box[4]; int rank, swizzle; bool valid; CUtensorMap map; };
+    static thread_local Entry cache[8] = {};
+    static thread_local unsigned next_slot = 0;
+    Entry key = {};
+    key.base = base; key.rank = rank; key.swizzle = (int)swizzle;
+    for (int i = 0; i < rank; ++i) { key.gdim[i] = gdim[i]; key.box[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) key.gstr[i] = gstride_bytes[i];
+    for (const Entry& e : cache)
+        if (e.valid && e.base == key.base && e.rank == key.rank && e.swizzle == key.swizzle && !memcmp(e.gdim, key.gdim, sizeof(key.gdim)) &&
+            !memcmp(e.gstr, key.gstr, sizeof(key.gstr)) && !memcmp(e.box, key.box, sizeof(key.box))) {
+            *map = e.map;
+            return 0;
+        }
+    if (int rc = get_encode_tiled()) return rc;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride_bytes, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(JBLAS_B200_ECUDA, "cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
+    Entry& slot = cache[next_slot++ % 8];
+    slot = key;
+    slot.map = *map;
+    slot.valid = true;
+    return 0;
+}
+
+// Tall-skinny Float64 (gemm_skinny.cuh): N <= 64, K a multiple of 8 with X resident in shared memory, aligned operands.
+using SK_n64 = SkinnyCfg<8, 12, 32, 3>;  // 12 warps, boxes of 16 rows x 32 k: 23.3 us at 65536 x 64 x 64 (profiles/r2_skinny_probe_v2.txt)
+using SK_n32 = SkinnyCfg<4, 12, 32, 3>;
+static constexpr int kSkinnyMaxK = 128, kSkinnyMaxN = 64;
+static bool skinny_shape_ok(int64_t M, int64_t N, int64_t K) { return M >= 1 && N >= 1 && N <= kSkinnyMaxN && K >= 8 && K <= kSkinnyMaxK && K % 8 == 0; }
+template <typename Cfg, bool ACC>
+static int launch_skinny_cfg(double* D, const double* A, const double* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx, cudaStream_t s,
+                             const double* Cin, int64_t ldc)
+{
+    CUtensorMap mapA, mapX;
+    {   // A as (m, s_lo, t, s_hi) with k = 8 s_hi + 4 s_lo + t; box = 16 rows x KC k
+        const cuuint64_t gdim[4] = {(cuuint64_t)M, 2, 4, (cuuint64_t)(K / 8)};
+        const cuuint64_t gstr[3] = {(cuuint64_t)(4 * lda * 8), (cuuint64_t)(lda * 8), (cuuint64_t)(8 * lda * 8)};
+        const cuuint32_t box[4] = {16, 2, 4, (cuuint32_t)(Cfg::KC / 8)};
+        if (int rc = make_tmap_nd(&mapA, A, 4, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
+    {   // X as (t, n, s) with k = 4 s + t: ONE box = the whole matrix in fragment-major order
+        const cuuint64_t gdim[3] = {4, (cuuint64_t)N, (cuuint64_t)(K / 4)};
+        const cuuint64_t gstr[2] = {(cuuint64_t)(ldx * 8), 32};
+        const cuuint32_t box[3] = {4, (cuuint32_t)Cfg::BN, (cuuint32_t)(K / 4)};
+        if (int rc = make_tmap_nd(&mapX, X, 3, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+    }
+    const int nblocks = (M + 15) / 16;
+    int grid = (nblocks + Cfg::WARPS - 1) / Cfg::WARPS;
+    if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
+    gemm_skinny_f64_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::smem(K), s>>>(mapA, mapX, D, M, N, K, ldd, Cin, ldc, nullptr);
+    return 0;
+}
+template <bool ACC>
+static int launch_skinny(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx, int, int, int, cudaStream_t s,
+                         const void* Cin, int64_t ldc)
+{
+    if (!skinny_shape_ok(M, N, K))
+        return fail(JBLAS_B200_EUNSUPPORTED, "the tall-skinny kernel takes N <= %d and K <= %d, K a multiple of 8 (got N=%d K=%d)", kSkinnyMaxN, kSkinnyMaxK, N, K);
+    if (N <= 32) return launch_skinny_cfg<SK_n32, ACC>((double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, s, (const double*)Cin, ldc);
+    return launch_skinny_cfg<SK_n64, ACC>((double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, s, (const double*)Cin, ldc);
+}
+static cudaError_t attr_skinny()
+{
+    cudaError_t e = cudaSuccess;
+    const int most = (int)SK_n64::smem(kSkinnyMaxK);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_f64_kernel<SK_n64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_f64_kernel<SK_n64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_f64_kernel<SK_n32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_f64_kernel<SK_n32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+    return e;
+}
 static int launch_needs_alignment(void*, const void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, int, int,
                                   cudaStream_t, const void*, int64_t)
 {
@@ -586,8 +663,11 @@ static const KernelInfo g_kernels[] = {
     /* 27 */ SIMT_F32X2_ENTRY("simt_f32x2_32x32x16_w2", F2_32x32_w2, 1.00f),
     /* 28 */ F32_TMA_ENTRY("simt_f32_tma_ffma2_128x256x32_s4", F32T_s4, 1.40f),
     /* 29 */ TF32X3_PAIR_ENTRY("tf32x3_tcgen05_2cta_f32_256x256x32_s3", X3_PAIR, 1.11f),  // 8192^3: 270.8 vs 243.7 TFLOP/s, 16384^3: 239 vs 214 (same box, incl. the split)
+    /* 30 */ {"dmma_skinny_f64_16x64_xres_w12", JBLAS_B200_DT_F64, FAM_DMMA, 16, 64, 32, 2, SK_n64::THREADS, SK_n64::smem(64), 1.0f, true, true, 1,
+              {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny<false>, launch_skinny<true>}}, attr_skinny, nullptr},
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
+static constexpr int kSkinnyKernel = 30;
 static int g_occ[NUM_KERNELS] = {0};  // measured residency (filled at init); 0 = unknown, the planner uses ctas_per_sm
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
 
@@ -615,7 +695,6 @@ static bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p)
 static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldx, const void* A, const void* X,
                      int selector, Plan* out)
 {
-    (void)K;
     const int num_sms = g_ctx.num_sms > 0 ? g_ctx.num_sms : 148;
     int family = -1, explicit_idx = -1;
     if (selector >= JBLAS_B200_EXPLICIT_BASE) {
@@ -637,8 +716,12 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
     out->aligned = is_aligned16(A) && is_aligned16(X) && (lda % vec == 0) && (ldx % vec == 0);
     int best = -1;
     double best_t = 0;
-    for (int i = 0; i < NUM_KERNELS; ++i) {
+    // Tall-skinny Float64 on the tensor pipe: X resident in shared memory, A streamed once by warp-private TMA pipelines
+    // (gemm_skinny.cuh).  Measured against the best tile kernel on cold operands: 23.3 vs 24.9 us at 65536 x 64 x 64.
+    if (explicit_idx < 0 && dtype == JBLAS_B200_DT_F64 && family == FAM_DMMA && out->aligned && skinny_shape_ok(M, N, K) && M >= 16384) best = kSkinnyKernel;
+    for (int i = 0; i < NUM_KERNELS && best != kSkinnyKernel; ++i) {
         const KernelInfo& k = g_kernels[i];
+        if (explicit_idx < 0 && i == kSkinnyKernel) continue;  // only through the shape rule above
         if (explicit_idx >= 0 ? (i != explicit_idx) : (k.dtype != dtype || k.family != family)) continue;
         if (explicit_idx < 0 && k.needs_aligned && !out->aligned && !k.has_ragged) continue;
         int64_t tiles = ((M + k.bm - 1) / k.bm) * ((N + k.bn - 1) / k.bn);

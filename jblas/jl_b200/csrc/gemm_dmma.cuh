@@ -28,6 +28,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// same, accumulator written from a separate start value (first k-step of a chain: no register initialisation pass)
+__device__ __forceinline__ void dmma884_from(double& d0, double& d1, double a, double b, double c0, double c1)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
 template <int WM, int WN, int BK_, int STAGES_>
 struct DmmaCfg {
     static constexpr int BM = WM * 64, BN = WN * 32, BK = BK_, STAGES = STAGES_;

@@ -438,8 +438,44 @@ def test_config_tall_skinny_65536x64x64(jb):
     A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
     want = oracle.oracle_gemm(A, X)
     assert bits_equal(_run_dev(jb, A, X, jb.F64_SIMT), want)
-    ok, worst = oracle.error_bound_ok(_run_dev(jb, A, X, jb.F64_AUTO), want, A, X)
-    assert ok, worst
+    assert jb.plan(M, K, N)["kernel"] == SKINNY  # AUTO: the dedicated tall-skinny kernel (X resident, A streamed once)
+    assert bits_equal(_run_dev(jb, A, X, jb.F64_AUTO), want)  # DMMA chains like the reference on B200: every bit
+
+
+SKINNY = "dmma_skinny_f64_16x64_xres_w12"
+
+
+@pytest.mark.parametrize("shape", [(65536, 64, 64), (20000, 72, 48), (16385, 8, 33), (100, 128, 64), (5000, 40, 17), (3000, 64, 32), (1, 8, 1),
+                                   (40000, 128, 64), (16 * 1776 + 5, 64, 64)], ids=lambda s: "x".join(map(str, s)))
+def test_tall_skinny_kernel_bit_identical(jb, shape):
+    """gemm_skinny.cuh forced on shapes around its limits: N < 64 (zero-filled X columns, guarded stores), N <= 32 (the
+    4-tile configuration), odd M (TMA zero-fills the missing rows of the last block, element-wise stores), K = 8 .. 128,
+    fewer blocks than warps, a block count that leaves a ragged tail of half-block items; overwrite, accumulate
+    (kernel! semantics) and a D whose leading dimension breaks the 16-byte stores."""
+    M, K, N = shape
+    sel = jb.EXPLICIT_BASE + jb.kernel_names().index(SKINNY)
+    ldA = M + (M & 1)  # the TMA path needs an even leading dimension
+    A, X = randn_f((M, K), ld=ldA), randn_f((K, N), seed=SEED_X)
+    Ad = np.asfortranarray(A)
+    want = oracle.oracle_gemm(Ad, X)
+    assert bits_equal(_run_dev(jb, A, X, sel), want)
+    assert bits_equal(_run_dev(jb, A, X, sel, ldd=M + 3 - (M & 1)), want)  # odd ldd: element-wise stores
+    D0 = randn_f((M, N), seed=5)
+    assert bits_equal(_run_dev(jb, A, X, sel, accumulate_into=D0), oracle.oracle_gemm(Ad, X, D0.copy(order="F"), accumulate=True))
+
+
+def test_tall_skinny_kernel_limits(jb):
+    sel = jb.EXPLICIT_BASE + jb.kernel_names().index(SKINNY)
+    A, X = randn_f((4096, 36)), randn_f((36, 64), seed=SEED_X)  # K not a multiple of 8
+    with pytest.raises(jb.JblasB200Error):
+        _run_dev(jb, A, X, sel)
+    A, X = randn_f((4096, 64)), randn_f((64, 72), seed=SEED_X)  # N > 64
+    with pytest.raises(jb.JblasB200Error):
+        _run_dev(jb, A, X, sel)
+    # AUTO: only tall shapes with a short contraction take it; everything else stays on the tile kernels
+    assert jb.plan(65536, 64, 64)["kernel"] == SKINNY and jb.plan(300000, 128, 40)["kernel"] == SKINNY
+    assert jb.plan(4096, 64, 64)["kernel"] != SKINNY and jb.plan(65536, 256, 64)["kernel"] != SKINNY and jb.plan(65536, 64, 128)["kernel"] != SKINNY
+    assert jb.plan(65535, 64, 64)["kernel"] != SKINNY  # odd leading dimension: the ragged producers of the tile kernels
 
 
 def _sampled_check(jb, n, dtype_name, selector, exact, extra_rel=0.0, tiles=()):

@@ -109,6 +109,235 @@ static void dmma_rate(int warps, int sms, double* out)
     fflush(stdout);
 }
 
+// The skinny kernel's k-step with operands re-loaded from (resident) shared memory every step, no global traffic: which part of
+// the instruction mix costs tensor-pipe time?  MI2 = pairs of 8-row tiles (one LDS.128 of A each), NI column tiles;
+// BMODE 0: one LDS.64 per B fragment, 1: one LDS.128 per two B fragments; NALU extra integer instructions per step.
+template <int MI2, int NI, int BMODE, int NALU>
+__global__ void __launch_bounds__(256, 1) dmma_lds_kernel(double* out, int iters)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    double* sd = reinterpret_cast<double*>(sm);
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sd[i] = 1.0 + 1e-9 * i;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t baseA = smem_u32(sd) + lane * 16, baseB = smem_u32(sd) + 8192 + lane * (BMODE ? 16 : 8);
+    double acc[2 * MI2][NI][2];
+#pragma unroll
+    for (int m = 0; m < 2 * MI2; ++m)
+#pragma unroll
+        for (int n = 0; n < NI; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+    double2 a[2][MI2];
+    double b[2][NI];
+    unsigned alu = threadIdx.x;
+    unsigned alu4[4] = {threadIdx.x, threadIdx.x + 1, threadIdx.x + 2, threadIdx.x + 3};
+    auto load = [&](int it, int which) {
+        const uint32_t off = (uint32_t)(it & 7) * 512;
+#pragma unroll
+        for (int m = 0; m < MI2; ++m)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(a[which][m].x), "=d"(a[which][m].y) : "r"(baseA + off + m * 4096));
+        if (BMODE == 0) {
+#pragma unroll
+            for (int n = 0; n < NI; ++n) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(b[which][n]) : "r"(baseB + off + n * 256));
+        } else {
+#pragma unroll
+            for (int n = 0; n < NI; n += 2)
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(b[which][n]), "=d"(b[which][n + 1]) : "r"(baseB + off + n * 256));
+        }
+    };
+    auto mma = [&](int which) {
+#pragma unroll
+        for (int n = 0; n < NI; ++n)
+#pragma unroll
+            for (int m = 0; m < MI2; ++m) {
+                dmma884(acc[2 * m][n][0], acc[2 * m][n][1], a[which][m].x, b[which][n]);
+                dmma884(acc[2 * m + 1][n][0], acc[2 * m + 1][n][1], a[which][m].y, b[which][n]);
+            }
+        if (NALU > 0) {
+#pragma unroll
+            for (int i = 0; i < NALU; ++i) asm volatile("xor.b32 %0, %0, %1;\n" : "+r"(alu) : "r"(0x9E3779B9u + i));
+        } else {  // negative: independent integer multiply-adds (IMAD: the FMA-side integer pipe), 4 chains
+#pragma unroll
+            for (int i = 0; i < -NALU; ++i) asm volatile("mad.lo.u32 %0, %0, %1, %2;\n" : "+r"(alu4[i & 3]) : "r"(0x9E3779B9u + i), "r"(i + 1));
+        }
+    };
+    load(0, 0);
+    for (int it = 0; it < iters; it += 2) {
+        load(it + 1, 1);
+        mma(0);
+        load(it + 2, 0);
+        mma(1);
+    }
+    double sacc = 0;
+#pragma unroll
+    for (int m = 0; m < 2 * MI2; ++m)
+#pragma unroll
+        for (int n = 0; n < NI; ++n) sacc += acc[m][n][0] + acc[m][n][1];
+    if (sacc == 123.456 || alu == 0x12345678u || (alu4[0] ^ alu4[1] ^ alu4[2] ^ alu4[3]) == 0x12345678u) out[0] = sacc;
+}
+template <int MI2, int NI, int BMODE, int NALU>
+static void dmma_lds(int warps, int sms, double* out)
+{
+    const int iters = 4000;
+    cudaFuncSetAttribute(dmma_lds_kernel<MI2, NI, BMODE, NALU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e9f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        dmma_lds_kernel<MI2, NI, BMODE, NALU><<<sms, warps * 32, 65536>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, dmma_lds_kernel<MI2, NI, BMODE, NALU>);
+    const double flops = 2.0 * 256 * 2 * MI2 * NI * iters * (double)sms * warps;
+    printf("dmma+lds: %d x %d tiles, B via %s, %2d extra ALU/step, %2d warps/SM, %3d regs: %6.2f TFLOP/s  (%s)\n", 2 * MI2, NI, BMODE ? "LDS.128" : "LDS.64 ", NALU, warps,
+           fa.numRegs, flops / (best * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
+    fflush(stdout);
+}
+
+// Item boundaries in the synthetic loop: every 16 k-steps of 8 DMMAs (one 16 x 32 item of K = 64) the warp does what the real
+// kernel does between items.  MODE 0: nothing (continuous stream); 1: SERIAL boundary -- lane 0 draws a ticket from a shared
+// counter (atomicAdd + shfl), a dependent shared-memory read stands in for the mbarrier wait, the first fragments are loaded with
+// their latency exposed, the finished accumulators are stored; 2: the same work, but the ticket/"wait"/first fragment loads are
+// issued one k-step BEFORE the boundary (nothing is waited for at the boundary itself), stores deferred by two steps.
+template <int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) dmma_item_kernel(double* out, int items, double* scratch)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    double* sd = reinterpret_cast<double*>(sm);
+    __shared__ int ctr;
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sd[i] = 1.0 + 1e-9 * i;
+    if (threadIdx.x == 0) ctr = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t baseA = smem_u32(sd) + lane * 16, baseB = smem_u32(sd) + 8192 + lane * 8;
+    constexpr int NI = 4;
+    double acc[2][2][NI][2];
+    double2 a[2];
+    double b[2][NI];
+    auto load = [&](int it, int which, uint32_t extra) {
+        const uint32_t off = (uint32_t)(it & 7) * 512 + extra;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(a[which].x), "=d"(a[which].y) : "r"(baseA + off));
+#pragma unroll
+        for (int n = 0; n < NI; ++n) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(b[which][n]) : "r"(baseB + off + n * 256));
+    };
+    auto mma = [&](double (&c)[2][NI][2], int which) {
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+            dmma884(c[0][n][0], c[0][n][1], a[which].x, b[which][n]);
+            dmma884(c[1][n][0], c[1][n][1], a[which].y, b[which][n]);
+        }
+    };
+    auto mma_first = [&](double (&c)[2][NI][2], int which) {
+        const double nz = -0.0;
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+            dmma884_from(c[0][n][0], c[0][n][1], a[which].x, b[which][n], nz, nz);
+            dmma884_from(c[1][n][0], c[1][n][1], a[which].y, b[which][n], nz, nz);
+        }
+    };
+    double* myout = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    auto store = [&](double (&c)[2][NI][2], int item) {
+        double* p = myout + (size_t)(item & 3) * gridDim.x * blockDim.x * 2 * 8;
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+            *reinterpret_cast<double2*>(p + (size_t)n * 2 * gridDim.x * blockDim.x * 2) = make_double2(c[0][n][0], c[1][n][0]);
+            *reinterpret_cast<double2*>(p + (size_t)(n * 2 + 1) * gridDim.x * blockDim.x * 2) = make_double2(c[0][n][1], c[1][n][1]);
+        }
+    };
+    auto ticket = [&]() -> uint32_t {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(&ctr, 1);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        uint32_t w;  // dependent shared-memory round trip: stands in for the mbarrier try_wait of the next box
+        asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(w) : "r"(smem_u32(sd) + ((uint32_t)v & 63u) * 4));
+        return (w & 1u) * 0u + ((uint32_t)v & 1u) * 16u * 0u;
+    };
+    if (MODE == 0) {
+        mma_first(acc[0], 0);
+        load(0, 0, 0);
+        for (int it = 0; it < items * 16; it += 2) {
+            load(it + 1, 1, 0);
+            mma(acc[0], 0);
+            load(it + 2, 0, 0);
+            mma(acc[0], 1);
+        }
+        store(acc[0], 0);
+    } else if (MODE == 1) {
+        for (int item = 0; item < items; ++item) {
+            const uint32_t extra = ticket();
+            load(0, 0, extra);
+            load(1, 1, extra);
+            mma_first(acc[0], 0);
+            load(2, 0, extra);
+            mma(acc[0], 1);
+            for (int it = 2; it < 16; it += 2) {
+                load(it + 1, 1, extra);
+                mma(acc[0], 0);
+                if (it + 2 < 16) load(it + 2, 0, extra);
+                mma(acc[0], 1);
+            }
+            store(acc[0], item);
+        }
+    } else {
+        uint32_t extra = ticket();
+        load(0, 0, extra);
+        for (int item = 0; item < items; item += 2) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                double(&c)[2][NI][2] = acc[half];
+                double(&pc)[2][NI][2] = acc[half ^ 1];
+                load(1, 1, extra);
+                mma_first(c, 0);
+                load(2, 0, extra);
+                mma(c, 1);
+                if (item + half > 0) store(pc, item + half - 1);
+                uint32_t next_extra = extra;
+                for (int it = 2; it < 16; it += 2) {
+                    load(it + 1, 1, extra);
+                    mma(c, 0);
+                    if (it == 12) next_extra = ticket();  // the next item's ticket and "wait": two k-steps before the boundary
+                    if (it + 2 < 16) load(it + 2, 0, extra);
+                    else load(0, 0, next_extra);          // first fragments of the NEXT item, one k-step ahead as everywhere else
+                    mma(c, 1);
+                }
+                extra = next_extra;
+            }
+        }
+        store(acc[1], items - 1);
+    }
+    double sacc = 0;
+#pragma unroll
+    for (int n = 0; n < NI; ++n) sacc += acc[0][0][n][0] + acc[1][1][n][1];
+    if (sacc == 123.456) out[0] = sacc;
+}
+template <int MODE, int WARPS>
+static void dmma_item(int sms, double* out, double* scratch)
+{
+    const int items = 256;
+    cudaFuncSetAttribute(dmma_item_kernel<MODE, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e9f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        dmma_item_kernel<MODE, WARPS><<<sms, WARPS * 32, 65536>>>(out, items, scratch);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, dmma_item_kernel<MODE, WARPS>);
+    const double flops = 2.0 * 256 * 8 * 16 * items * (double)sms * WARPS;
+    printf("dmma items of 16 k-steps x 8 DMMA, boundary mode %d (%s), %2d warps/SM, %3d regs: %6.2f TFLOP/s  (%s)\n", MODE,
+           MODE == 0 ? "none" : MODE == 1 ? "serial" : "pipelined across the boundary", WARPS, fa.numRegs, flops / (best * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
+    fflush(stdout);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static CUtensorMap make_map(const double* A, int M, int K, int64_t lda, int KC)
@@ -152,6 +381,7 @@ template <typename Cfg>
 static void run(const char* name, int M, int N, int K, std::vector<double*>& As, double* X, std::vector<double*>& Ds, double* Dref, int ctas)
 {
     const size_t smem = Cfg::smem(K);
+    if (smem > 232448) { printf("%-28s needs %zu bytes of shared memory: skipped\n", name, smem); return; }
     auto kern = gemm_skinny_f64_kernel<Cfg, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncAttributes fa;
@@ -189,7 +419,7 @@ static void run(const char* name, int M, int N, int K, std::vector<double*>& As,
         cudaMemcpy(ht.data(), tr, ht.size() * 8, cudaMemcpyDeviceToHost);
         unsigned long long t0 = ~0ull;
         for (int w = 0; w < nw; ++w) if (ht[w * 12] && ht[w * 12] < t0) t0 = ht[w * 12];
-        const char* names[12] = {"entry", "X staged", "first box", "block 0 stored", "block 1 stored", "block 2 stored", "block 3 stored", "block 4", "block 5", "block 6", "block 7", "block 8"};
+        const char* names[12] = {"entry", "X staged", "first box", "item 0 multiplied", "item 1", "item 2", "item 3", "item 4", "item 5", "item 6", "item 7", "item 8"};
         for (int sl = 0; sl < 12; ++sl) {
             double mn = 1e18, mx = 0, sum = 0; int cnt = 0;
             for (int w = 0; w < nw; ++w) { unsigned long long v = ht[w * 12 + sl]; if (!v) continue; double d = (double)(v - t0) / 1e3; mn = d < mn ? d : mn; mx = d > mx ? d : mx; sum += d; ++cnt; }
@@ -226,19 +456,41 @@ int main(int argc, char** argv)
     chain_ref<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(Dref, As[0], X, M, N, K, M, M, K);
     cudaDeviceSynchronize();
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (only == -4) {
+        double* scratch;
+        cudaMalloc(&scratch, (size_t)sms * 512 * 2 * 8 * 4 * 8 + 4096);
+        dmma_item<0, 8>(sms, Dref, scratch); dmma_item<1, 8>(sms, Dref, scratch); dmma_item<2, 8>(sms, Dref, scratch);
+        dmma_item<0, 12>(sms, Dref, scratch); dmma_item<1, 12>(sms, Dref, scratch); dmma_item<2, 12>(sms, Dref, scratch);
+        dmma_item<0, 16>(sms, Dref, scratch); dmma_item<1, 16>(sms, Dref, scratch); dmma_item<2, 16>(sms, Dref, scratch);
+        return 0;
+    }
+    if (only == -3) {
+        for (int w : {8, 12}) {
+            dmma_lds<1, 8, 0, 0>(w, sms, Dref);
+            dmma_lds<1, 8, 1, 0>(w, sms, Dref);
+            dmma_lds<1, 8, 0, 30>(w, sms, Dref);
+            dmma_lds<1, 8, 0, -16>(w, sms, Dref);
+            dmma_lds<1, 8, 0, -48>(w, sms, Dref);
+            dmma_lds<1, 8, 0, -96>(w, sms, Dref);
+            dmma_lds<1, 4, 0, -24>(w, sms, Dref);
+            dmma_lds<1, 4, 0, -48>(w, sms, Dref);
+            dmma_lds<2, 8, 0, 0>(w, sms, Dref);
+            dmma_lds<2, 8, 1, 0>(w, sms, Dref);
+            dmma_lds<2, 4, 0, 0>(w, sms, Dref);
+            dmma_lds<1, 4, 0, 0>(w, sms, Dref);
+        }
+        return 0;
+    }
     if (only == -2) {
         for (int w : {4, 8, 16}) { dmma_pattern<0, 8>(w, sms, Dref); dmma_pattern<1, 8>(w, sms, Dref); dmma_pattern<0, 4>(w, sms, Dref); dmma_pattern<1, 4>(w, sms, Dref); }
         for (int w : {4, 8}) { dmma_rate<4>(w, sms, Dref); dmma_rate<8>(w, sms, Dref); dmma_rate<16>(w, sms, Dref); dmma_rate<32>(w, sms, Dref); }
         return 0;
     }
     printf("M %d N %d K %d, %d SMs, %d rotating sets (%.0f MB)\n", M, N, K, sms, R, R * ((double)M * K + (double)M * N) * 8 / 1e6);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 0>>("w8 kc64 plain halves", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 1>>("w8 kc64 stagger", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 2>>("w8 kc64 late 2nd box", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 12, 32, 3>>("w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 3>>("w8 kc64 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 32, 3>>("w8 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 16, 16, 3>>("w16 kc16 stagger+late", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 16, 32, 3>>("w16 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
-    if (only < 0 || only == idx++) run<SkinnyCfg<8, 12, 32, 3>>("w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 0>>("w8 kc64 plain halves", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<4, 12, 32, 3>>("ni4 w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     return 0;
 }
