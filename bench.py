@@ -785,7 +785,7 @@ def run_e2e(args, jb, _lib, sg, A, X, D, dtype, M, K, world, rank, dev, flops_st
         assert not np.isnan(Dh).any()
         h2d, d2h = Ah.nbytes + Xh.nbytes, Dh.nbytes
         return {"value": flops_step * steps / sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": steps, "ms_per_step": 1e3 * sec / steps, "api": "jblas_b200_gemm_f64 (host pointers, pinned by jblas_b200_host_register)"}
+                "steps": steps, "ms_per_step": 1e3 * sec / steps, "api": f"jblas_b200_gemm_{'f64' if dtype == 'float64' else 'f32'} (host pointers, pinned by jblas_b200_host_register)"}
     # N > 1: the SINGLE-PROCESS multi-GPU entry of the C ABI, jblas_b200_mgpu_gemm_* -- what a Julia `jmul!(D, A, X; gpus = N)`
     # hits: one host process, the whole A / X / D in pinned host memory, N GPUs driven from it.  Rank 0 makes the call on
     # all N GPUs; the other ranks of this torchrun job hold no GPU work meanwhile and wait on a HOST-side (gloo) barrier.

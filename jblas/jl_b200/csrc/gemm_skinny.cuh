@@ -57,7 +57,8 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
 
 template <int NI_, int WARPS_, int KC_ = 64, int FLAGS_ = 3>
 struct SkinnyCfg {
-    static constexpr int FLAGS = FLAGS_;  // bit 0: stagger the half items (above); bit 1: second box requested after X has landed
+    static constexpr int FLAGS = FLAGS_;  // bit 0: stagger the half items (above); bit 1: second box requested after X has landed;
+                                          // probe-only ablations (results are wrong): bit 2 = no stores of D, bit 3 = no A boxes (stale shared memory)
     static constexpr int NI = NI_, WARPS = WARPS_, THREADS = WARPS_ * 32, BN = NI_ * 8;
     static constexpr int KC = KC_;                    // k chunk of one TMA box (multiple of 8)
     static constexpr int BOX_BYTES = 16 * KC * 8;     // 16 rows x KC columns of doubles
@@ -141,7 +142,7 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     __syncwarp();
     int ij = 0, ic = 0;  // next box to REQUEST: item ij, chunk ic
     auto request = [&](int buf) {
-        if (ij < nitems && lane == 0) {
+        if (ij < nitems && lane == 0 && !(Cfg::FLAGS & 8)) {
             int blk, half;
             item(ij, blk, half);
             mbar_expect_tx(&full[buf], Cfg::BOX_BYTES);
@@ -209,7 +210,7 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 for (int c = 0; c < 2; ++c) acc[0][ni][c] = acc[1][ni][c] = -0.0;
         }
         for (int chunk = 0; chunk < nchunks; ++chunk) {
-            mbar_wait(&full[buf], phase);
+            if (!(Cfg::FLAGS & 8)) mbar_wait(&full[buf], phase);
             if (done == 0 && chunk == 0) stamp(2);
             const int s0 = chunk * (KC / 4);
             const int steps = min(ksteps - s0, KC / 4);  // even: K % 8 == 0
@@ -240,7 +241,12 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             request(buf);
             if (++buf == NBUF) { buf = 0; phase ^= 1; }
         }
-        if (fast) {
+        if (Cfg::FLAGS & 4) {  // keep the accumulators alive without storing them
+            double sum = 0;
+#pragma unroll
+            for (int ni = 0; ni < NIC; ++ni) sum += acc[0][ni][0] * acc[1][ni][1];
+            if (sum == 1.2345678) D[m] = sum;
+        } else if (fast) {
             double* p = D + (int64_t)ncol0 * ldd + m;
 #pragma unroll
             for (int ni = 0; ni < NIC; ++ni)

@@ -492,5 +492,9 @@ int main(int argc, char** argv)
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 32, 3>>("w8 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 0>>("w8 kc64 plain halves", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<4, 12, 32, 3>>("ni4 w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
+    if (only == idx++) run<SkinnyCfg<8, 12, 32, 3 + 4>>("w12 kc32 NO STORES", M, N, K, As, X, Ds, Dref, sms);
+    if (only == idx++) run<SkinnyCfg<8, 12, 32, 3 + 8>>("w12 kc32 NO A BOXES", M, N, K, As, X, Ds, Dref, sms);
+    if (only == idx++) run<SkinnyCfg<8, 12, 32, 3 + 12>>("w12 kc32 NO STORES, NO A", M, N, K, As, X, Ds, Dref, sms);
+    if (only == idx++) run<SkinnyCfg<8, 8, 64, 3 + 12>>("w8 kc64 NO STORES, NO A", M, N, K, As, X, Ds, Dref, sms);
     return 0;
 }
