@@ -58,7 +58,8 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
 template <int NI_, int WARPS_, int KC_ = 64, int FLAGS_ = 3>
 struct SkinnyCfg {
     static constexpr int FLAGS = FLAGS_;  // bit 0: stagger the half items (above); bit 1: second box requested after X has landed;
-                                          // probe-only ablations (results are wrong): bit 2 = no stores of D, bit 3 = no A boxes (stale shared memory)
+                                          // probe-only ablations (results are wrong): bit 2 = no stores of D, bit 3 = no A boxes (stale shared memory);
+                                          // bit 4: anti-phase handshake between the warps of an SM sub-partition (below)
     static constexpr int NI = NI_, WARPS = WARPS_, THREADS = WARPS_ * 32, BN = NI_ * 8;
     static constexpr int KC = KC_;                    // k chunk of one TMA box (multiple of 8)
     static constexpr int BOX_BYTES = 16 * KC * 8;     // 16 rows x KC columns of doubles
@@ -68,7 +69,7 @@ struct SkinnyCfg {
     // X lives in shared memory FRAGMENT-MAJOR, sX[s][n][t]: the 32 doubles lane (g, t) = X[4s + t][8 ni + g] of k-step s, column
     // tile ni are contiguous in lane order, so every fragment load is base + lane*8 + immediate (conflict-free)
     static size_t x_bytes(int K) { return (size_t)(K / 4) * NI * 256; }
-    static size_t smem(int K) { return (size_t)WARPS * NBUF * BOX_BYTES + x_bytes(K) + (WARPS * NBUF + 1) * sizeof(uint64_t) + 1024; }
+    static size_t smem(int K) { return (size_t)WARPS * NBUF * BOX_BYTES + x_bytes(K) + (WARPS * NBUF + 1 + (WARPS + 1) / 2) * sizeof(uint64_t) + 1024; }
 };
 
 template <int V>
@@ -100,6 +101,17 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     const int ksteps = K >> 2;  // K % 8 == 0 (host-checked): whole pairs of k-steps
     uint64_t* bars = reinterpret_cast<uint64_t*>(sX + (size_t)ksteps * NI * 32);
     uint64_t* full = bars + warp * NBUF;
+
+    // Anti-phase handshake (FLAGS bit 4).  The G warps that share an SM sub-partition (warp, warp + 4, ...) drift into lock-step
+    // and then reach their item boundaries together, leaving the DMMA pipe without work (measured).  With the
+    // handshake, the warp of rank r starts its item j only when the warp of rank r - 1 is 1/G of the way through ITS item j
+    // (rank 0: through item j - 1 of rank G - 1): the boundaries of the G warps stay 1/G of a period apart.  Progress counters
+    // (in G-ths of an item) live in shared memory; a warp that has run out of items publishes "infinitely far".
+    constexpr int G = Cfg::WARPS / 4;
+    volatile int* prog = reinterpret_cast<volatile int*>(bars + Cfg::WARPS * NBUF + 1);
+    if (tid < Cfg::WARPS) prog[tid] = 0;
+    const int rank = warp >> 2, prev_warp = ((rank + G - 1) % G) * 4 + (warp & 3);
+    const int prog_scale = (G << 16) / (ksteps > 0 ? ksteps : 1);  // k-steps -> G-ths of an item, 16.16 fixed point
 
     const int nblocks = (M + 15) >> 4, nchunks = (K + KC - 1) / KC;
     const int W = gridDim.x * Cfg::WARPS;
@@ -172,6 +184,11 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     auto process = [&](auto ni0_c, auto nic_c, int blk) {
         constexpr int NI0 = decltype(ni0_c)::value, NIC = decltype(nic_c)::value;
         double acc[2][NIC][2];
+        if ((Cfg::FLAGS & 16) && G > 1) {
+            const int need = G * (rank ? done : done - 1) + 1;
+            if (need > 0)
+                while (prog[prev_warp] < need) {}
+        }
         const int m = blk * 16 + 2 * g;
         const int ncol0 = NI0 * 8 + 2 * t;  // this lane's first column; the others are ncol0 + 8 ni + c
         const bool fast = vec_ok && blk * 16 + 16 <= M;
@@ -236,6 +253,10 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 mma(0);
                 if (s + 2 < steps) load(s + 2, 0);
                 mma(1);
+                if ((Cfg::FLAGS & 16) && lane == 0) {
+                    int frac = ((s0 + s + 2) * prog_scale) >> 16;
+                    prog[warp] = G * done + (frac < G ? frac : G - 1);
+                }
             }
             __syncwarp();  // every lane has read the box: it may be overwritten
             request(buf);
@@ -267,6 +288,7 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         }
         stamp(3 + done);
         ++done;
+        if ((Cfg::FLAGS & 16) && lane == 0) prog[warp] = G * done;
     };
     for (int j = 0; j < nitems; ++j) {
         int blk, half;
@@ -274,6 +296,179 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         if (half < 0) process(IntC<0>{}, IntC<NI>{}, blk);
         else if (half == 0) process(IntC<0>{}, IntC<NI / 2>{}, blk);
         else process(IntC<NI / 2>{}, IntC<NI / 2>{}, blk);
+    }
+    if ((Cfg::FLAGS & 16) && lane == 0) prog[warp] = 0x7fffffff;
+}
+
+// =====================================================================================================================
+// X IN REGISTERS (K = 32 or 64, N <= 64): the variant the per-instruction profile of the kernel above asked for.
+//
+// ncu, one warp per SM sub-partition (profiles/r2_ncu_skinny_lone_warp.txt): the warp is never throttled by the DMMA pipe; its
+// time goes to the fixed issue cadence of its own instructions -- a DMMA.8x8x4 holds the warp for ~16-18 clk and every LDS
+// (0.56 per DMMA above: eight X fragments + one A pair per k-step), its write-after-read scoreboard waits and the loop
+// arithmetic ADD to that instead of overlapping with it: 72 % of the pipe for a lone warp, 80 % for two, 82 % for three.
+// X is the same for every row block, so here it does not come from shared memory at all: each warp owns ONE half of the
+// columns (32 = 4 column tiles) for the whole kernel and keeps its X fragments -- KSTEPS x 4 doubles per lane, 128
+// registers for K = 64 -- in REGISTERS, loaded once from global memory.  The k loop is straight-line code: per k-step one
+// LDS.128 (rows 2g, 2g+1 of A) and 8 DMMAs (0.125 loads per DMMA).  Everything else is the design above: warp-private
+// TMA boxes (16 rows x K), 128B-swizzled 4-D layout, -0.0 start, 16-byte stores straight from the accumulators.  Items are
+// (row block, column half); the two warps (2i, 2i+1) of a CTA walk the same blocks, so the second fetch of a box is an L2
+// hit, and 4096 blocks over 592 warps per half are 6.92 rounds of 2048 pipe-clocks: 1 % of round quantisation instead of 13 %.
+// =====================================================================================================================
+template <int KSTEPS_, int WARPS_, int NBUF_ = 2>
+struct SkinnyRegCfg {
+    static constexpr int KSTEPS = KSTEPS_, K = 4 * KSTEPS_, WARPS = WARPS_, THREADS = WARPS_ * 32, NBUF = NBUF_;
+    static constexpr int NG = 4, BN = 64;            // column tiles per warp item, columns covered by the two halves
+    static constexpr int BOX_BYTES = 16 * K * 8;     // 16 rows x K columns of doubles
+    static_assert(KSTEPS_ % 2 == 0 && BOX_BYTES % 1024 == 0, "a box is a whole number of swizzle atoms");
+    static constexpr size_t SMEM = (size_t)WARPS * NBUF * BOX_BYTES + (size_t)WARPS * NBUF * sizeof(uint64_t) + 1024;
+};
+
+template <typename Cfg, bool ACC>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+gemm_skinny_xreg_f64_kernel(const __grid_constant__ CUtensorMap mapA, const double* __restrict__ X, int64_t ldx, double* __restrict__ D, int M, int N,
+                            int64_t ldd, const double* __restrict__ Cin, int64_t ldc)
+{
+    constexpr int KSTEPS = Cfg::KSTEPS, NG = Cfg::NG, NBUF = Cfg::NBUF;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // swizzle atoms
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    unsigned char* myA = base + (size_t)warp * NBUF * Cfg::BOX_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)Cfg::WARPS * NBUF * Cfg::BOX_BYTES) + warp * NBUF;
+
+    // this warp's column half and its place among the warps of that half (CTA index fastest: neighbouring blocks are in flight together)
+    const int halves = N > 32 ? 2 : 1;
+    const int half = halves == 2 ? (warp & 1) : 0;
+    const int hw = (halves == 2 ? (warp >> 1) : warp) * gridDim.x + blockIdx.x;
+    const int HW = (Cfg::WARPS / halves) * gridDim.x;
+    const int nblocks = (M + 15) >> 4;
+
+    if (lane == 0) {
+        if (warp == 0) tma_prefetch_desc(&mapA);
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    int rq = hw;  // next block to request
+    auto request = [&](int buf) {
+        if (rq < nblocks && lane == 0) {
+            mbar_expect_tx(&full[buf], Cfg::BOX_BYTES);
+            tma_load_4d(myA + buf * Cfg::BOX_BYTES, &mapA, &full[buf], rq * 16, 0, 0, 0);
+        }
+        rq += HW;
+    };
+    request(0);
+    // X fragments of this warp's columns: lane (g, t) holds X[4s + t][32 half + 8 ni + g] for every k-step s and column tile ni.
+    // Columns >= N read as 0 (their accumulators are never stored).
+    double xr[KSTEPS][NG];
+    {
+        const double* xp = X + t;
+#pragma unroll
+        for (int ni = 0; ni < NG; ++ni) {
+            const int n = 32 * half + 8 * ni + g;
+            const double* col = xp + (int64_t)n * ldx;
+#pragma unroll
+            for (int s = 0; s < KSTEPS; ++s) xr[s][ni] = n < N ? __ldg(col + 4 * s) : 0.0;
+        }
+    }
+#pragma unroll
+    for (int b = 1; b < NBUF; ++b) request(b);  // after the X loads: first boxes are served ahead of the later ones
+
+    // rows (2g, 2g+1) of column k = 4s + t of a box: row R = 8 (s >> 1) + 2t + (s & 1), chunk g ^ (R & 7)
+    const uint32_t sA0 = smem_u32(myA);
+    const uint32_t offA[2] = {(uint32_t)((2 * t) * 128 + ((g ^ (2 * t)) << 4)), (uint32_t)((2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4))};
+    const bool vec_ok = (ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 &&
+                        (!ACC || ((ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(Cin) & 15) == 0));
+    const int ncol0 = 32 * half + 2 * t;  // this lane's first column; the others are ncol0 + 8 ni + c
+    const bool cols_full = 32 * half + 32 <= N;
+
+    // (Tried and measured to change nothing: software-pipelining the loop ACROSS items -- first fragment of the next item and the
+    // wait for its box before the last k-step, stores of the previous item behind the second k-step, two accumulator sets.  The
+    // per-item instructions cost the warp the same issue time wherever they stand; only the other warp of the sub-partition
+    // hides them: tensor pipe 78 % with one warp per sub-partition, 90 % with two, profiles/r2_ncu_skinny_xreg_*.txt.)
+    int buf = 0;
+    uint32_t phase = 0;
+    for (int blk = hw; blk < nblocks; blk += HW) {
+        const int m = blk * 16 + 2 * g;
+        const bool fast = vec_ok && blk * 16 + 16 <= M;
+        double acc[2][NG][2];
+        if constexpr (ACC) {
+#pragma unroll
+            for (int ni = 0; ni < NG; ++ni)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int n = ncol0 + ni * 8 + c;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (n < N) {
+                        const double* p = Cin + (size_t)n * ldc + m;
+                        if (fast) {
+                            v = *reinterpret_cast<const double2*>(p);
+                        } else {
+                            if (m < M) v.x = p[0];
+                            if (m + 1 < M) v.y = p[1];
+                        }
+                    }
+                    acc[0][ni][c] = v.x;
+                    acc[1][ni][c] = v.y;
+                }
+        }
+        mbar_wait(&full[buf], phase);
+        const uint32_t pa = sA0 + buf * Cfg::BOX_BYTES;
+        // A fragments two k-steps ahead in FOUR register pairs: a load never overwrites a pair the DMMAs just issued still read
+        double2 a[4];
+        auto load = [&](int s) {
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(a[s & 3].x), "=d"(a[s & 3].y) : "r"(pa + offA[s & 1] + (s >> 1) * 1024));
+        };
+        load(0);
+        load(1);
+#pragma unroll
+        for (int s = 0; s < KSTEPS; ++s) {
+            if (s + 2 < KSTEPS) load(s + 2);
+            if (!ACC && s == 0) {  // the chain starts from -0.0: no accumulator initialisation pass
+                const double nz = -0.0;
+#pragma unroll
+                for (int ni = 0; ni < NG; ++ni) {
+                    dmma884_from(acc[0][ni][0], acc[0][ni][1], a[0].x, xr[0][ni], nz, nz);
+                    dmma884_from(acc[1][ni][0], acc[1][ni][1], a[0].y, xr[0][ni], nz, nz);
+                }
+            } else {
+#pragma unroll
+                for (int ni = 0; ni < NG; ++ni) {
+                    dmma884(acc[0][ni][0], acc[0][ni][1], a[s & 3].x, xr[s][ni]);
+                    dmma884(acc[1][ni][0], acc[1][ni][1], a[s & 3].y, xr[s][ni]);
+                }
+            }
+        }
+        __syncwarp();  // every lane has read the box: it may be overwritten
+        request(buf);
+        if (++buf == NBUF) { buf = 0; phase ^= 1; }
+        if (fast && cols_full) {  // 8 16-byte stores off one pointer, no predicates
+            double* p = D + (int64_t)ncol0 * ldd + m;
+            const int64_t ldd8 = 8 * ldd;
+#pragma unroll
+            for (int ni = 0; ni < NG; ++ni) {
+                *reinterpret_cast<double2*>(p) = make_double2(acc[0][ni][0], acc[1][ni][0]);
+                *reinterpret_cast<double2*>(p + ldd) = make_double2(acc[0][ni][1], acc[1][ni][1]);
+                p += ldd8;
+            }
+        } else {
+#pragma unroll
+            for (int ni = 0; ni < NG; ++ni)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int n = ncol0 + ni * 8 + c;
+                    if (n >= N) continue;
+                    double* p = D + (size_t)n * ldd + m;
+                    if (fast) {
+                        *reinterpret_cast<double2*>(p) = make_double2(acc[0][ni][c], acc[1][ni][c]);
+                    } else {
+                        if (m < M) p[0] = acc[0][ni][c];
+                        if (m + 1 < M) p[1] = acc[1][ni][c];
+                    }
+                }
+        }
     }
 }
 

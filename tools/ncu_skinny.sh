@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu --set full of the tall-skinny warp-private kernel in the probe harness (variant index $1, rows $2), cold operands
+# ncu --set full of a tall-skinny probe variant (index $1, rows $2), cold operands; summary on the box, report kept for the source page
 set -u
 mkdir -p gpurun_out
 V=${1:-1}

@@ -1,0 +1,8 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gemm_gpu.py -m gpu -x -q -k "skinny" > gpurun_out/pytest_skinny.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_skinny.log
+timeout 600 python tools/skinny_compare.py > gpurun_out/skinny_compare.txt 2>&1; cat gpurun_out/skinny_compare.txt | tail -14 | cut -c1-330
+timeout 300 ncu --set full --clock-control none --import-source on -k "regex:gemm_skinny" -s 7 -c 1 -o gpurun_out/prof_skinny_lib -f python tools/ncu_target.py float64 65536 64 64 auto 12 6 > gpurun_out/ncu_skinny_lib.log 2>&1; echo "ncu skinny rc=$?"
+python tools/ncu_summary.py gpurun_out/prof_skinny_lib.ncu-rep gpurun_out/sum_skinny_lib.txt "FP64 65536x64x64 AUTO = dmma_skinny_f64_16x32_xreg_w8, COLD operands (6 rotating sets = 403 MB, 8th launch captured)" > /dev/null 2>&1
+grep -E "kernel:|time_duration|tensor_cycles|dram__bytes|cycles_elapsed" gpurun_out/sum_skinny_lib.txt

@@ -15,6 +15,7 @@ jb.init(0)
 names = jb.kernel_names()
 tile = {n: jb.EXPLICIT_BASE + i for i, n in enumerate(names) if n in ("dmma_tma_f64_64x32x32_s4_x2", "dmma_tma_f64_64x64x32_s3_x2", "dmma_tma_f64_64x64x64_s3")}
 skinny = jb.EXPLICIT_BASE + names.index("dmma_skinny_f64_16x64_xres_w12")
+xreg = jb.EXPLICIT_BASE + names.index("dmma_skinny_f64_16x32_xreg_w8")
 
 
 def timeit(fn, bufs, reps=200):
@@ -34,11 +35,13 @@ def timeit(fn, bufs, reps=200):
 
 
 for (M, N, K) in [(65536, 64, 64), (16384, 64, 64), (32768, 64, 64), (131072, 64, 64), (300000, 64, 64), (1000000, 64, 64), (65536, 32, 64), (65536, 64, 128),
-                  (65536, 48, 72), (262144, 16, 32)]:
+                  (65536, 48, 72), (65536, 48, 64), (262144, 16, 32), (131072, 64, 32)]:
     nbytes = (M * K + K * N + M * N) * 8
     sets = max(2, min(12, -(-400_000_000 // nbytes)))
     bufs = [(jb.empty_colmajor(M, N, "float64"), jb.mrandn(M, K, "float64", seed=2 * i + 1), jb.mrandn(K, N, "float64", seed=2 * i + 2)) for i in range(sets)]
-    row = {"skinny": timeit(lambda D, A, X: api._gemm(D, A, X, False, skinny), bufs)}
+    row = {"skinny": timeit(lambda D, A, X: api._gemm(D, A, X, False, skinny), bufs) if K % 8 == 0 and K <= 128 else float("nan")}
+    if K in (32, 64):
+        row["xreg"] = timeit(lambda D, A, X: api._gemm(D, A, X, False, xreg), bufs)
     for n, sel in tile.items():
         row[n[13:]] = timeit(lambda D, A, X, sel=sel: api._gemm(D, A, X, False, sel), bufs)
     row["cuBLAS"] = timeit(lambda D, A, X: torch.matmul(A, X, out=D.t().contiguous().t() if False else None), bufs)

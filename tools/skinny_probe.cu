@@ -380,7 +380,8 @@ static CUtensorMap make_map_x(const double* X, int K, int N, int64_t ldx, int BN
 template <typename Cfg>
 static void run(const char* name, int M, int N, int K, std::vector<double*>& As, double* X, std::vector<double*>& Ds, double* Dref, int ctas)
 {
-    const size_t smem = Cfg::smem(K);
+    size_t smem = Cfg::smem(K);
+    if (getenv("SKINNY_PAD")) smem += (size_t)atoi(getenv("SKINNY_PAD"));  // e.g. force one CTA per SM for a 4-warp configuration
     if (smem > 232448) { printf("%-28s needs %zu bytes of shared memory: skipped\n", name, smem); return; }
     auto kern = gemm_skinny_f64_kernel<Cfg, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -438,6 +439,45 @@ static void run(const char* name, int M, int N, int K, std::vector<double*>& As,
     fflush(stdout);
 }
 
+template <typename Cfg>
+static void run_xreg(const char* name, int M, int N, int K, std::vector<double*>& As, double* X, std::vector<double*>& Ds, double* Dref, int ctas)
+{
+    if (K != Cfg::K) { printf("%-28s needs K = %d: skipped\n", name, Cfg::K); return; }
+    const size_t smem = Cfg::SMEM;
+    if (smem > 232448) { printf("%-28s needs %zu bytes of shared memory: skipped\n", name, smem); return; }
+    auto kern = gemm_skinny_xreg_f64_kernel<Cfg, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    const int R = (int)As.size();
+    std::vector<CUtensorMap> maps(R);
+    for (int i = 0; i < R; ++i) maps[i] = make_map(As[i], M, K, M, Cfg::K);
+    for (int i = 0; i < R; ++i) { cudaMemset(Ds[i], 0xff, (size_t)M * N * 8); kern<<<ctas, Cfg::THREADS, smem>>>(maps[i], X, K, Ds[i], M, N, M, nullptr, 0); }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%-28s FAILED: %s\n", name, cudaGetErrorString(e)); exit(1); }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = 120;
+    float best = 1e9f;
+    for (int outer = 0; outer < 3; ++outer) {
+        cudaEventRecord(e0);
+        for (int i = 0; i < reps; ++i) kern<<<ctas, Cfg::THREADS, smem>>>(maps[i % R], X, K, Ds[i % R], M, N, M, nullptr, 0);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms / reps < best) best = ms / reps;
+    }
+    std::vector<double> h((size_t)M * N), r((size_t)M * N);
+    cudaMemcpy(h.data(), Ds[0], h.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(r.data(), Dref, r.size() * 8, cudaMemcpyDeviceToHost);
+    const bool same = memcmp(h.data(), r.data(), h.size() * 8) == 0;
+    const double us = best * 1e3, bytes = ((double)M * K + (double)K * N + (double)M * N) * 8, flops = 2.0 * M * N * K;
+    printf("%-28s ctas %4d regs %3d smem %6zu  %7.2f us  %6.2f TFLOP/s  %5.2f TB/s  %s\n", name, ctas, fa.numRegs, smem, us, flops / us / 1e6,
+           bytes / us / 1e6, same ? "bit-identical" : "MISMATCH");
+    fflush(stdout);
+}
+
 int main(int argc, char** argv)
 {
     int M = argc > 1 ? atoi(argv[1]) : 65536, N = argc > 2 ? atoi(argv[2]) : 64, K = argc > 3 ? atoi(argv[3]) : 64;
@@ -487,11 +527,25 @@ int main(int argc, char** argv)
         return 0;
     }
     printf("M %d N %d K %d, %d SMs, %d rotating sets (%.0f MB)\n", M, N, K, sms, R, R * ((double)M * K + (double)M * N) * 8 / 1e6);
+    if (only == -5 || only == 100) run_xreg<SkinnyRegCfg<16, 8, 2>>("xreg k64 w8 nbuf2", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 101) run_xreg<SkinnyRegCfg<16, 8, 3>>("xreg k64 w8 nbuf3", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 102) run_xreg<SkinnyRegCfg<16, 12, 2>>("xreg k64 w12 nbuf2", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 103) run_xreg<SkinnyRegCfg<16, 10, 2>>("xreg k64 w10 nbuf2", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 104) run_xreg<SkinnyRegCfg<16, 4, 2>>("xreg k64 w4 nbuf2 (lone warps)", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 105) run_xreg<SkinnyRegCfg<8, 12, 2>>("xreg k32 w12 nbuf2", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only >= 100) return 0;
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 12, 32, 3>>("w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 3>>("w8 kc64 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 32, 3>>("w8 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 0>>("w8 kc64 plain halves", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<4, 12, 32, 3>>("ni4 w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 3 + 16>>("w8 kc64 stagger+late+antiphase", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 2 + 16>>("w8 kc64 late+antiphase", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 12, 32, 3 + 16>>("w12 kc32 stagger+late+antiphase", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 12, 32, 2 + 16>>("w12 kc32 late+antiphase", M, N, K, As, X, Ds, Dref, sms);
+    if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 32, 2 + 16>>("w8 kc32 late+antiphase", M, N, K, As, X, Ds, Dref, sms);
+    if (only == idx++) run<SkinnyCfg<8, 4, 64, 2>>("w4 kc64 late (SKINNY_PAD=40000: one warp per sub-partition)", M, N, K, As, X, Ds, Dref, sms);
+    if (only == idx++) run<SkinnyCfg<8, 4, 64, 2 + 12>>("w4 kc64 late NO STORES, NO A", M, N, K, As, X, Ds, Dref, sms);
     if (only == idx++) run<SkinnyCfg<8, 12, 32, 3 + 4>>("w12 kc32 NO STORES", M, N, K, As, X, Ds, Dref, sms);
     if (only == idx++) run<SkinnyCfg<8, 12, 32, 3 + 8>>("w12 kc32 NO A BOXES", M, N, K, As, X, Ds, Dref, sms);
     if (only == idx++) run<SkinnyCfg<8, 12, 32, 3 + 12>>("w12 kc32 NO STORES, NO A", M, N, K, As, X, Ds, Dref, sms);
