@@ -1998,6 +1998,22 @@ static int fastmul_batched_host(T* D, const T* A, const T* X, int64_t M, int64_t
         if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * (size_t)rows, kind, st);  // dense: one run
         return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, (size_t)rows, kind, st);  // strided batch: gaps untouched
     };
+    // Success or not, nothing may stay in flight when the call returns: the copies reference the caller's host buffers and the
+    // shared workspaces (every early return below runs this), and a failed call must not leave a stale time behind.
+    struct Drain {
+        cudaStream_t a, b, c;
+        float* last_ms;
+        bool ok = false;
+        ~Drain()
+        {
+            if (ok) return;
+            cudaStreamSynchronize(a);
+            cudaStreamSynchronize(b);
+            cudaStreamSynchronize(c);
+            cudaGetLastError();
+            *last_ms = 0.f;
+        }
+    } drain{os, cs, ks, &g_ctx.last_ms};
     CUDA_TRY(cudaEventRecord(g_ctx.ev0, cs));
     int64_t c = 0;
     for (int64_t b0 = 0; b0 < batch; b0 += nb, ++c) {
@@ -2021,6 +2037,7 @@ static int fastmul_batched_host(T* D, const T* A, const T* X, int64_t M, int64_t
     CUDA_TRY(cudaStreamSynchronize(os));
     CUDA_TRY(cudaStreamSynchronize(cs));
     CUDA_TRY(cudaStreamSynchronize(ks));
+    drain.ok = true;
     cudaEventElapsedTime(&g_ctx.last_ms, g_ctx.ev0, g_ctx.ev1);
     return 0;
 }

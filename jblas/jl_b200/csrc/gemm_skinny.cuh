@@ -315,10 +315,10 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 // (row block, column half); the two warps (2i, 2i+1) of a CTA walk the same blocks, so the second fetch of a box is an L2
 // hit, and 4096 blocks over 592 warps per half are 6.92 rounds of 2048 pipe-clocks: 1 % of round quantisation instead of 13 %.
 // =====================================================================================================================
-template <int KSTEPS_, int WARPS_, int NBUF_ = 2>
+template <int KSTEPS_, int WARPS_, int NBUF_ = 2, int NG_ = 4>
 struct SkinnyRegCfg {
     static constexpr int KSTEPS = KSTEPS_, K = 4 * KSTEPS_, WARPS = WARPS_, THREADS = WARPS_ * 32, NBUF = NBUF_;
-    static constexpr int NG = 4, BN = 64;            // column tiles per warp item, columns covered by the two halves
+    static constexpr int NG = NG_, BN = 64;          // column tiles per warp item (4: two column halves; 2: four quarters), columns covered
     static constexpr int BOX_BYTES = 16 * K * 8;     // 16 rows x K columns of doubles
     static_assert(KSTEPS_ % 2 == 0 && BOX_BYTES % 1024 == 0, "a box is a whole number of swizzle atoms");
     static constexpr size_t SMEM = (size_t)WARPS * NBUF * BOX_BYTES + (size_t)WARPS * NBUF * sizeof(uint64_t) + 1024;
@@ -338,9 +338,10 @@ gemm_skinny_xreg_f64_kernel(const __grid_constant__ CUtensorMap mapA, const doub
     uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)Cfg::WARPS * NBUF * Cfg::BOX_BYTES) + warp * NBUF;
 
     // this warp's column half and its place among the warps of that half (CTA index fastest: neighbouring blocks are in flight together)
-    const int halves = N > 32 ? 2 : 1;
-    const int half = halves == 2 ? (warp & 1) : 0;
-    const int hw = (halves == 2 ? (warp >> 1) : warp) * gridDim.x + blockIdx.x;
+    constexpr int GW = 8 * NG;                       // columns per group
+    const int halves = min((N + GW - 1) / GW, 64 / GW);  // column groups that exist ("halves" when NG = 4)
+    const int half = warp % halves;
+    const int hw = (warp / halves) * gridDim.x + blockIdx.x;
     const int HW = (Cfg::WARPS / halves) * gridDim.x;
     const int nblocks = (M + 15) >> 4;
 
@@ -367,7 +368,7 @@ gemm_skinny_xreg_f64_kernel(const __grid_constant__ CUtensorMap mapA, const doub
         const double* xp = X + t;
 #pragma unroll
         for (int ni = 0; ni < NG; ++ni) {
-            const int n = 32 * half + 8 * ni + g;
+            const int n = GW * half + 8 * ni + g;
             const double* col = xp + (int64_t)n * ldx;
 #pragma unroll
             for (int s = 0; s < KSTEPS; ++s) xr[s][ni] = n < N ? __ldg(col + 4 * s) : 0.0;
@@ -381,8 +382,8 @@ gemm_skinny_xreg_f64_kernel(const __grid_constant__ CUtensorMap mapA, const doub
     const uint32_t offA[2] = {(uint32_t)((2 * t) * 128 + ((g ^ (2 * t)) << 4)), (uint32_t)((2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4))};
     const bool vec_ok = (ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 &&
                         (!ACC || ((ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(Cin) & 15) == 0));
-    const int ncol0 = 32 * half + 2 * t;  // this lane's first column; the others are ncol0 + 8 ni + c
-    const bool cols_full = 32 * half + 32 <= N;
+    const int ncol0 = GW * half + 2 * t;  // this lane's first column; the others are ncol0 + 8 ni + c
+    const bool cols_full = GW * half + GW <= N;
 
     // (Tried and measured to change nothing: software-pipelining the loop ACROSS items -- first fragment of the next item and the
     // wait for its box before the last k-step, stores of the previous item behind the second k-step, two accumulator sets.  The

@@ -533,6 +533,9 @@ int main(int argc, char** argv)
     if (only == -5 || only == 103) run_xreg<SkinnyRegCfg<16, 10, 2>>("xreg k64 w10 nbuf2", M, N, K, As, X, Ds, Dref, sms);
     if (only == -5 || only == 104) run_xreg<SkinnyRegCfg<16, 4, 2>>("xreg k64 w4 nbuf2 (lone warps)", M, N, K, As, X, Ds, Dref, sms);
     if (only == -5 || only == 105) run_xreg<SkinnyRegCfg<8, 12, 2>>("xreg k32 w12 nbuf2", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 106) run_xreg<SkinnyRegCfg<16, 16, 2, 2>>("xreg k64 w16 quarters", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 107) run_xreg<SkinnyRegCfg<16, 12, 2, 2>>("xreg k64 w12 quarters", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 108) run_xreg<SkinnyRegCfg<16, 8, 2, 2>>("xreg k64 w8 quarters", M, N, K, As, X, Ds, Dref, sms);
     if (only == -5 || only >= 100) return 0;
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 12, 32, 3>>("w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 3>>("w8 kc64 stagger+late", M, N, K, As, X, Ds, Dref, sms);
