@@ -478,6 +478,59 @@ static cudaError_t attr_skinny_xreg()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_xreg_f64_kernel<SKR_k32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKR_k32::SMEM);
     return e;
 }
+// X in registers, boxes shared by a team of four quarter-column warps (gemm_skinny.cuh, third kernel): K = 64 or 32 exactly.
+// Launched with programmatic stream serialisation: a following launch of the same kind is scheduled while this one runs and
+// waits (griddepcontrol.wait) before its first global access -- 1.7 us less per call in back-to-back streams of products.
+using SKT_k64 = SkinnyTeamCfg<16, 16, 3, 2>;
+using SKT_k32 = SkinnyTeamCfg<8, 16, 3, 2>;
+template <typename Cfg, bool ACC>
+static int launch_skinny_team_cfg(double* D, const double* A, const double* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx, cudaStream_t s,
+                                  const double* Cin, int64_t ldc)
+{
+    CUtensorMap mapA;
+    const cuuint64_t gdim[4] = {(cuuint64_t)M, 2, 4, (cuuint64_t)(K / 8)};
+    const cuuint64_t gstr[3] = {(cuuint64_t)(4 * lda * 8), (cuuint64_t)(lda * 8), (cuuint64_t)(8 * lda * 8)};
+    const cuuint32_t box[4] = {16, 2, 4, (cuuint32_t)(K / 8)};
+    if (int rc = make_tmap_nd(&mapA, A, 4, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    const int nblocks = (M + 15) / 16;
+    int grid = (nblocks + Cfg::TEAMS - 1) / Cfg::TEAMS;
+    if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
+    static int no_pdl = -1;
+    if (no_pdl < 0) {
+        const char* e = getenv("JBLAS_B200_NO_PDL");
+        no_pdl = (e && atoi(e)) ? 1 : 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_skinny_team_f64_kernel<Cfg, ACC>, mapA, X, ldx, D, M, N, ldd, Cin, ldc));
+    return 0;
+}
+template <bool ACC>
+static int launch_skinny_team(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx, int, int, int, cudaStream_t s,
+                              const void* Cin, int64_t ldc)
+{
+    if (!skinny_xreg_shape_ok(M, N, K))
+        return fail(JBLAS_B200_EUNSUPPORTED, "the team tall-skinny kernel takes N <= %d and K = 32 or 64 (got N=%d K=%d)", kSkinnyMaxN, N, K);
+    if (K == 32) return launch_skinny_team_cfg<SKT_k32, ACC>((double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, s, (const double*)Cin, ldc);
+    return launch_skinny_team_cfg<SKT_k64, ACC>((double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, s, (const double*)Cin, ldc);
+}
+static cudaError_t attr_skinny_team()
+{
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<SKT_k64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKT_k64::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<SKT_k64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKT_k64::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<SKT_k32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKT_k32::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<SKT_k32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKT_k32::SMEM);
+    return e;
+}
 static cudaError_t attr_skinny()
 {
     cudaError_t e = cudaSuccess;
@@ -704,9 +757,11 @@ static const KernelInfo g_kernels[] = {
               {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny<false>, launch_skinny<true>}}, attr_skinny, nullptr},
     /* 31 */ {"dmma_skinny_f64_16x32_xreg_w8", JBLAS_B200_DT_F64, FAM_DMMA, 16, 32, 64, 2, SKR_k64::THREADS, SKR_k64::SMEM, 1.0f, true, true, 1,
               {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny_xreg<false>, launch_skinny_xreg<true>}}, attr_skinny_xreg, nullptr},
+    /* 32 */ {"dmma_skinny_f64_16x16_xreg_team_w16", JBLAS_B200_DT_F64, FAM_DMMA, 16, 64, 64, 3, SKT_k64::THREADS, SKT_k64::SMEM, 1.0f, true, true, 1,
+              {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny_team<false>, launch_skinny_team<true>}}, attr_skinny_team, nullptr},
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
-static constexpr int kSkinnyKernel = 30, kSkinnyXregKernel = 31;
+static constexpr int kSkinnyKernel = 30, kSkinnyXregKernel = 31, kSkinnyTeamKernel = 32;
 static int g_occ[NUM_KERNELS] = {0};  // measured residency (filled at init); 0 = unknown, the planner uses ctas_per_sm
 #define JBLAS_B200_EXPLICIT_BASE 100 /* selector 100+i forces g_kernels[i] (tuning / tests) */
 
@@ -753,22 +808,24 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
     }
     const int vec = dtype == JBLAS_B200_DT_F64 ? 2 : 4;
     out->aligned = is_aligned16(A) && is_aligned16(X) && (lda % vec == 0) && (ldx % vec == 0);
-    if (explicit_idx == 31) out->aligned = is_aligned16(A) && (lda % vec == 0);  // the X-in-registers kernel reads X element-wise: only A goes through TMA
+    if (explicit_idx == 31 || explicit_idx == 32) out->aligned = is_aligned16(A) && (lda % vec == 0);  // the X-in-registers kernels read X element-wise: only A goes through TMA
     int best = -1;
     double best_t = 0;
     // Tall-skinny Float64 on the tensor pipe: X resident in shared memory, A streamed once by warp-private TMA pipelines
     // (gemm_skinny.cuh).  Measured against the best tile kernel on cold operands: 23.3 vs 24.9 us at 65536 x 64 x 64.
     // K = 64 or 32: the variant that keeps the X fragments in registers (22.6 us; tensor pipe 90 % in the steady state).
     if (explicit_idx < 0 && dtype == JBLAS_B200_DT_F64 && family == FAM_DMMA && out->aligned && M >= 16384) {
-        // measured (profiles/r2_skinny_compare.txt): the register variant wins for both column halves (N > 32) up to ~500k rows
-        // (65536: 22.6 vs 24.2 us, 300000: 76.7 vs 82.0); for N <= 32 and beyond 2^19 rows (10^6: 293 vs 258 us) the shared-memory one
-        if (skinny_xreg_shape_ok(M, N, K) && N > 32 && M <= (1 << 19)) best = kSkinnyXregKernel;
+        // measured (profiles/r2_skinny_compare.txt): with both column halves in use (N > 32) the register variants win, and the
+        // team kernel (one box per row block, four quarter-column warps, 16 warps per SM) is the one that stays at the algorithmic
+        // DRAM traffic for any M (10^6 rows: 239 us against 293 for private boxes and 258 for the shared-memory variant);
+        // for N <= 32 the shared-memory variant with its 4-tile configuration is faster (14.9 vs 16.4 us at 65536 x 32 x 64)
+        if (skinny_xreg_shape_ok(M, N, K) && N > 32) best = kSkinnyTeamKernel;
         else if (skinny_shape_ok(M, N, K)) best = kSkinnyKernel;
     }
     const bool by_shape_rule = best >= 0;
     for (int i = 0; i < NUM_KERNELS && !by_shape_rule; ++i) {
         const KernelInfo& k = g_kernels[i];
-        if (explicit_idx < 0 && (i == kSkinnyKernel || i == kSkinnyXregKernel)) continue;  // only through the shape rule above
+        if (explicit_idx < 0 && (i == kSkinnyKernel || i == kSkinnyXregKernel || i == kSkinnyTeamKernel)) continue;  // only through the shape rule above
         if (explicit_idx >= 0 ? (i != explicit_idx) : (k.dtype != dtype || k.family != family)) continue;
         if (explicit_idx < 0 && k.needs_aligned && !out->aligned && !k.has_ragged) continue;
         int64_t tiles = ((M + k.bm - 1) / k.bm) * ((N + k.bn - 1) / k.bn);

@@ -473,4 +473,184 @@ gemm_skinny_xreg_f64_kernel(const __grid_constant__ CUtensorMap mapA, const doub
     }
 }
 
+// =====================================================================================================================
+// X IN REGISTERS, BOXES SHARED BY A TEAM OF WARPS.  The kernel above fetches every A box once per column group; the second fetch
+// is an L2 hit only while the warps that share a row block stay close in time and A fits in L2: at 10^6 rows the two halves
+// drift apart and DRAM traffic doubles (293 us against 258), and with four column QUARTERS per block -- 56 fewer registers,
+// shorter start-up, 21.5 us at 65536 rows -- it quadruples (512 us).  Here the TEAM = 64 / (8 NG) warps that cover the column
+// groups of a row block consume the SAME box: member 0 requests it (one TMA per block), every member waits on the box's `full`
+// mbarrier, multiplies its own columns and arrives on the box's `empty` mbarrier; member 0 re-uses a buffer only when its
+// `empty` phase has completed, and it asks one item later than it could, so that it practically never waits for a team mate.
+// With quarters a warp needs ~120 registers: 16 warps per SM (four per sub-partition) hide each other's non-DMMA instructions.
+// =====================================================================================================================
+template <int KSTEPS_, int WARPS_, int NBUF_ = 3, int NG_ = 2>
+struct SkinnyTeamCfg {
+    static constexpr int KSTEPS = KSTEPS_, K = 4 * KSTEPS_, WARPS = WARPS_, THREADS = WARPS_ * 32, NBUF = NBUF_, NG = NG_;
+    static constexpr int TEAM = 64 / (8 * NG_), TEAMS = WARPS_ / TEAM, BN = 64;
+    static constexpr int BOX_BYTES = 16 * K * 8;
+    static_assert(WARPS_ % TEAM == 0 && NBUF_ >= 2, "whole teams, at least two boxes per team");
+    static_assert(KSTEPS_ % 2 == 0 && BOX_BYTES % 1024 == 0, "a box is a whole number of swizzle atoms");
+    static constexpr size_t SMEM = (size_t)TEAMS * NBUF * BOX_BYTES + (size_t)TEAMS * NBUF * 2 * sizeof(uint64_t) + 1024;
+};
+
+template <typename Cfg, bool ACC>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+gemm_skinny_team_f64_kernel(const __grid_constant__ CUtensorMap mapA, const double* __restrict__ X, int64_t ldx, double* __restrict__ D, int M, int N,
+                            int64_t ldd, const double* __restrict__ Cin, int64_t ldc)
+{
+    constexpr int KSTEPS = Cfg::KSTEPS, NG = Cfg::NG, NBUF = Cfg::NBUF, TEAM = Cfg::TEAM, GW = 8 * NG;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // swizzle atoms
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int team = warp / TEAM, member = warp % TEAM;
+    unsigned char* teamA = base + (size_t)team * NBUF * Cfg::BOX_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)Cfg::TEAMS * NBUF * Cfg::BOX_BYTES) + team * 2 * NBUF;
+    uint64_t* empty = full + NBUF;
+
+    const int nblocks = (M + 15) >> 4;
+    const int tg = team * gridDim.x + blockIdx.x, TG = Cfg::TEAMS * gridDim.x;  // CTA index fastest: neighbouring blocks are in flight together
+    const bool has_cols = GW * member < N;  // a member without columns only keeps the box protocol going
+
+    // Programmatic dependent launch: when the host launches this kernel with programmatic stream serialisation, the NEXT kernel
+    // of the stream may be scheduled while this one runs (its CTAs take the SMs as they become free) and does its prologue --
+    // barrier init, tensor-map prefetch -- early; griddepcontrol.wait then holds it until every earlier kernel has completed
+    // and flushed, BEFORE its first global-memory access.  Without the launch attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    if (member == 0 && lane == 0) {
+        if (warp == 0) tma_prefetch_desc(&mapA);
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(&full[b], 1);
+            mbar_init(&empty[b], TEAM);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();  // the team's barriers exist before any member waits on them
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    // item i of the team = block tg + i TG, box buffer i % NBUF, parity (i / NBUF) & 1 on both barriers of that buffer
+    auto request = [&](int i) {  // member 0 only
+        const int blk = tg + i * TG;
+        if (blk < nblocks && lane == 0) {
+            const int b = i % NBUF;
+            mbar_expect_tx(&full[b], Cfg::BOX_BYTES);
+            tma_load_4d(teamA + b * Cfg::BOX_BYTES, &mapA, &full[b], blk * 16, 0, 0, 0);
+        }
+    };
+    if (member == 0) request(0);
+    // X fragments of this member's columns: lane (g, t) holds X[4s + t][GW member + 8 ni + g]; columns >= N read as 0
+    double xr[KSTEPS][NG];
+    {
+        const double* xp = X + t;
+#pragma unroll
+        for (int ni = 0; ni < NG; ++ni) {
+            const int n = GW * member + 8 * ni + g;
+            const double* col = xp + (int64_t)n * ldx;
+#pragma unroll
+            for (int s = 0; s < KSTEPS; ++s) xr[s][ni] = n < N ? __ldg(col + 4 * s) : 0.0;
+        }
+    }
+    if (member == 0) {
+#pragma unroll
+        for (int b = 1; b < NBUF; ++b) request(b);  // after the X loads: first boxes are served ahead of the later ones
+    }
+
+    const uint32_t sA0 = smem_u32(teamA);
+    const uint32_t offA[2] = {(uint32_t)((2 * t) * 128 + ((g ^ (2 * t)) << 4)), (uint32_t)((2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4))};
+    const bool vec_ok = (ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 &&
+                        (!ACC || ((ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(Cin) & 15) == 0));
+    const int ncol0 = GW * member + 2 * t;
+    const bool cols_full = GW * member + GW <= N;
+
+    for (int i = 0, blk = tg; blk < nblocks; ++i, blk += TG) {
+        const int b = i % NBUF;
+        const uint32_t par = (uint32_t)(i / NBUF) & 1u;
+        const int m = blk * 16 + 2 * g;
+        const bool fast = vec_ok && blk * 16 + 16 <= M;
+        double acc[2][NG][2];
+        if constexpr (ACC) {
+#pragma unroll
+            for (int ni = 0; ni < NG; ++ni)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int n = ncol0 + ni * 8 + c;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (n < N) {
+                        const double* p = Cin + (size_t)n * ldc + m;
+                        if (fast) {
+                            v = *reinterpret_cast<const double2*>(p);
+                        } else {
+                            if (m < M) v.x = p[0];
+                            if (m + 1 < M) v.y = p[1];
+                        }
+                    }
+                    acc[0][ni][c] = v.x;
+                    acc[1][ni][c] = v.y;
+                }
+        }
+        mbar_wait(&full[b], par);
+        if (has_cols) {
+            const uint32_t pa = sA0 + b * Cfg::BOX_BYTES;
+            double2 a[4];
+            auto load = [&](int s) {
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(a[s & 3].x), "=d"(a[s & 3].y) : "r"(pa + offA[s & 1] + (s >> 1) * 1024));
+            };
+            load(0);
+            load(1);
+#pragma unroll
+            for (int s = 0; s < KSTEPS; ++s) {
+                if (s + 2 < KSTEPS) load(s + 2);
+                if (!ACC && s == 0) {  // the chain starts from -0.0: no accumulator initialisation pass
+                    const double nz = -0.0;
+#pragma unroll
+                    for (int ni = 0; ni < NG; ++ni) {
+                        dmma884_from(acc[0][ni][0], acc[0][ni][1], a[0].x, xr[0][ni], nz, nz);
+                        dmma884_from(acc[1][ni][0], acc[1][ni][1], a[0].y, xr[0][ni], nz, nz);
+                    }
+                } else {
+#pragma unroll
+                    for (int ni = 0; ni < NG; ++ni) {
+                        dmma884(acc[0][ni][0], acc[0][ni][1], a[s & 3].x, xr[s][ni]);
+                        dmma884(acc[1][ni][0], acc[1][ni][1], a[s & 3].y, xr[s][ni]);
+                    }
+                }
+            }
+        }
+        __syncwarp();  // every lane of this member has read the box
+        if (lane == 0) mbar_arrive(&empty[b]);
+        // member 0: the buffer of the PREVIOUS item gets item i - 1 + NBUF once the whole team has released it
+        if (member == 0 && i >= 1) {
+            mbar_wait(&empty[(i - 1) % NBUF], (uint32_t)((i - 1) / NBUF) & 1u);
+            request(i - 1 + NBUF);
+        }
+        if (has_cols) {
+            if (fast && cols_full) {  // 2 NG 16-byte stores off one pointer, no predicates
+                double* p = D + (int64_t)ncol0 * ldd + m;
+                const int64_t ldd8 = 8 * ldd;
+#pragma unroll
+                for (int ni = 0; ni < NG; ++ni) {
+                    *reinterpret_cast<double2*>(p) = make_double2(acc[0][ni][0], acc[1][ni][0]);
+                    *reinterpret_cast<double2*>(p + ldd) = make_double2(acc[0][ni][1], acc[1][ni][1]);
+                    p += ldd8;
+                }
+            } else {
+#pragma unroll
+                for (int ni = 0; ni < NG; ++ni)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int n = ncol0 + ni * 8 + c;
+                        if (n >= N) continue;
+                        double* p = D + (size_t)n * ldd + m;
+                        if (fast) {
+                            *reinterpret_cast<double2*>(p) = make_double2(acc[0][ni][c], acc[1][ni][c]);
+                        } else {
+                            if (m < M) p[0] = acc[0][ni][c];
+                            if (m + 1 < M) p[1] = acc[1][ni][c];
+                        }
+                    }
+            }
+        }
+    }
+}
+
 }  // namespace jb

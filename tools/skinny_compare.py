@@ -16,6 +16,7 @@ names = jb.kernel_names()
 tile = {n: jb.EXPLICIT_BASE + i for i, n in enumerate(names) if n in ("dmma_tma_f64_64x32x32_s4_x2", "dmma_tma_f64_64x64x32_s3_x2", "dmma_tma_f64_64x64x64_s3")}
 skinny = jb.EXPLICIT_BASE + names.index("dmma_skinny_f64_16x64_xres_w12")
 xreg = jb.EXPLICIT_BASE + names.index("dmma_skinny_f64_16x32_xreg_w8")
+team = jb.EXPLICIT_BASE + names.index("dmma_skinny_f64_16x16_xreg_team_w16")
 
 
 def timeit(fn, bufs, reps=200):
@@ -42,6 +43,7 @@ for (M, N, K) in [(65536, 64, 64), (16384, 64, 64), (32768, 64, 64), (131072, 64
     row = {"skinny": timeit(lambda D, A, X: api._gemm(D, A, X, False, skinny), bufs) if K % 8 == 0 and K <= 128 else float("nan")}
     if K in (32, 64):
         row["xreg"] = timeit(lambda D, A, X: api._gemm(D, A, X, False, xreg), bufs)
+        row["team"] = timeit(lambda D, A, X: api._gemm(D, A, X, False, team), bufs)
     for n, sel in tile.items():
         row[n[13:]] = timeit(lambda D, A, X, sel=sel: api._gemm(D, A, X, False, sel), bufs)
     row["cuBLAS"] = timeit(lambda D, A, X: torch.matmul(A, X, out=D.t().contiguous().t() if False else None), bufs)

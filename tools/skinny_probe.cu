@@ -439,13 +439,15 @@ static void run(const char* name, int M, int N, int K, std::vector<double*>& As,
     fflush(stdout);
 }
 
-template <typename Cfg>
+template <typename Cfg, bool TEAM_KERNEL = false>
 static void run_xreg(const char* name, int M, int N, int K, std::vector<double*>& As, double* X, std::vector<double*>& Ds, double* Dref, int ctas)
 {
     if (K != Cfg::K) { printf("%-28s needs K = %d: skipped\n", name, Cfg::K); return; }
     const size_t smem = Cfg::SMEM;
     if (smem > 232448) { printf("%-28s needs %zu bytes of shared memory: skipped\n", name, smem); return; }
-    auto kern = gemm_skinny_xreg_f64_kernel<Cfg, false>;
+    void (*kern)(const CUtensorMap, const double*, int64_t, double*, int, int, int64_t, const double*, int64_t);
+    if constexpr (TEAM_KERNEL) kern = gemm_skinny_team_f64_kernel<Cfg, false>;
+    else kern = gemm_skinny_xreg_f64_kernel<Cfg, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, kern);
@@ -460,9 +462,22 @@ static void run_xreg(const char* name, int M, int N, int K, std::vector<double*>
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int reps = 120;
     float best = 1e9f;
+    const bool pdl = getenv("SKINNY_PDL") != nullptr;  // programmatic dependent launch between the back-to-back launches
     for (int outer = 0; outer < 3; ++outer) {
         cudaEventRecord(e0);
-        for (int i = 0; i < reps; ++i) kern<<<ctas, Cfg::THREADS, smem>>>(maps[i % R], X, K, Ds[i % R], M, N, M, nullptr, 0);
+        for (int i = 0; i < reps; ++i) {
+            if (pdl) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                cudaLaunchKernelEx(&cfg, kern, maps[i % R], (const double*)X, (int64_t)K, Ds[i % R], M, N, (int64_t)M, (const double*)nullptr, (int64_t)0);
+            } else {
+                kern<<<ctas, Cfg::THREADS, smem>>>(maps[i % R], X, K, Ds[i % R], M, N, M, nullptr, 0);
+            }
+        }
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -536,6 +551,16 @@ int main(int argc, char** argv)
     if (only == -5 || only == 106) run_xreg<SkinnyRegCfg<16, 16, 2, 2>>("xreg k64 w16 quarters", M, N, K, As, X, Ds, Dref, sms);
     if (only == -5 || only == 107) run_xreg<SkinnyRegCfg<16, 12, 2, 2>>("xreg k64 w12 quarters", M, N, K, As, X, Ds, Dref, sms);
     if (only == -5 || only == 108) run_xreg<SkinnyRegCfg<16, 8, 2, 2>>("xreg k64 w8 quarters", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 109) run_xreg<SkinnyRegCfg<16, 8, 3, 2>>("xreg k64 w8 quarters nbuf3", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 110) run_xreg<SkinnyRegCfg<16, 12, 2, 2>>("xreg k64 w12 quarters", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 111) run_xreg<SkinnyRegCfg<16, 4, 2, 2>>("xreg k64 w4 quarters (lone)", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 120) run_xreg<SkinnyTeamCfg<16, 16, 3, 2>, true>("team k64 w16 quarters nbuf3", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 121) run_xreg<SkinnyTeamCfg<16, 16, 2, 2>, true>("team k64 w16 quarters nbuf2", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 122) run_xreg<SkinnyTeamCfg<16, 12, 3, 2>, true>("team k64 w12 quarters nbuf3", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 123) run_xreg<SkinnyTeamCfg<16, 8, 3, 2>, true>("team k64 w8 quarters nbuf3", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 124) run_xreg<SkinnyTeamCfg<16, 8, 3, 4>, true>("team k64 w8 halves nbuf3", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 125) run_xreg<SkinnyTeamCfg<16, 16, 4, 2>, true>("team k64 w16 quarters nbuf4", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 126) run_xreg<SkinnyTeamCfg<8, 16, 3, 2>, true>("team k32 w16 quarters nbuf3", M, N, K, As, X, Ds, Dref, sms);
     if (only == -5 || only >= 100) return 0;
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 12, 32, 3>>("w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 3>>("w8 kc64 stagger+late", M, N, K, As, X, Ds, Dref, sms);
