@@ -578,7 +578,10 @@ def run_gpu(args):
             "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic N(0,1), device-generated Philox (mrandn analogue), seeds jBLA/jBLA+1",
             "config": {"workload": desc, "M": M, "K": K, "N_total": n_total, "N_per_gpu": sg.shard_cols, "kernel_selector": args.kernel,
                        "parallelism": f"column-shard x{world}" + (f", A broadcast ({sg.bcast}) in {len(sg.panels)} K-panels (first {sg.panels[0][1] - sg.panels[0][0]}, then {args.panel_k})" if world > 1 else ""),
-                       "l2": f"inputs larger than L2: A+X+D = {(M * K + K * sg.shard_cols + M * sg.shard_cols) * es / 2**20:.0f} MiB per GPU vs 126 MB L2"},
+                       "l2": (f"inputs larger than L2: A+X+D = {(M * K + K * sg.shard_cols + M * sg.shard_cols) * es / 2**20:.0f} MiB per GPU vs 126 MB L2"
+                              if (M * K + K * sg.shard_cols + M * sg.shard_cols) * es > 2 * 126e6 else
+                              f"L2-WARM and host-call bound: A+X+D = {(M * K + K * sg.shard_cols + M * sg.shard_cols) * es / 2**20:.0f} MiB per GPU fit the 126 MB L2 and one step is one "
+                              "Python call; the cold-operand figure of this config (rotating sets > L2, 200 back-to-back launches) is the other_configs entry of the default line")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "parity_check": parity, "other_configs": other, "strong_c5": strong_c5,
             "build": dict(build.build_info(), mode=build.LAST_BUILD_MODE,

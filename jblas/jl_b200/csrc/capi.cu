@@ -375,6 +375,29 @@ static cudaError_t attr_dmma_tma_ragged()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     return e;
 }
+// Launch with programmatic stream serialisation (the kernel calls griddepcontrol.wait before its first global access): the next
+// such launch on the stream is scheduled while this one runs.  JBLAS_B200_NO_PDL=1 launches plainly (A/B measurements).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t s, Args... args)
+{
+    static int no_pdl = -1;
+    if (no_pdl < 0) {
+        const char* e = getenv("JBLAS_B200_NO_PDL");
+        no_pdl = (e && atoi(e)) ? 1 : 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // General tiled tensor map (rank 3 or 4, Float64) with a small per-thread cache, as make_tmap_2d.
 static int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstride_bytes, const cuuint32_t* box,
                         CUtensorMapSwizzle swizzle)
@@ -429,7 +452,7 @@ static int launch_skinny_cfg(double* D, const double* A, const double* X, int M,
     const int nblocks = (M + 15) / 16;
     int grid = (nblocks + Cfg::WARPS - 1) / Cfg::WARPS;
     if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
-    gemm_skinny_f64_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::smem(K), s>>>(mapA, mapX, D, M, N, K, ldd, Cin, ldc, nullptr);
+    CUDA_TRY(launch_pdl(gemm_skinny_f64_kernel<Cfg, ACC>, grid, Cfg::THREADS, Cfg::smem(K), s, mapA, mapX, D, M, N, K, ldd, Cin, ldc, (unsigned long long*)nullptr));
     return 0;
 }
 template <bool ACC>
@@ -457,7 +480,7 @@ static int launch_skinny_xreg_cfg(double* D, const double* A, const double* X, i
     const int items = ((M + 15) / 16) * (N > 32 ? 2 : 1);
     int grid = (items + Cfg::WARPS - 1) / Cfg::WARPS;
     if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
-    gemm_skinny_xreg_f64_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mapA, X, ldx, D, M, N, ldd, Cin, ldc);
+    CUDA_TRY(launch_pdl(gemm_skinny_xreg_f64_kernel<Cfg, ACC>, grid, Cfg::THREADS, Cfg::SMEM, s, mapA, X, ldx, D, M, N, ldd, Cin, ldc));
     return 0;
 }
 template <bool ACC>
@@ -495,22 +518,7 @@ static int launch_skinny_team_cfg(double* D, const double* A, const double* X, i
     const int nblocks = (M + 15) / 16;
     int grid = (nblocks + Cfg::TEAMS - 1) / Cfg::TEAMS;
     if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
-    static int no_pdl = -1;
-    if (no_pdl < 0) {
-        const char* e = getenv("JBLAS_B200_NO_PDL");
-        no_pdl = (e && atoi(e)) ? 1 : 0;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_skinny_team_f64_kernel<Cfg, ACC>, mapA, X, ldx, D, M, N, ldd, Cin, ldc));
+    CUDA_TRY(launch_pdl(gemm_skinny_team_f64_kernel<Cfg, ACC>, grid, Cfg::THREADS, Cfg::SMEM, s, mapA, X, ldx, D, M, N, ldd, Cin, ldc));
     return 0;
 }
 template <bool ACC>

@@ -91,6 +91,9 @@ gemm_skinny_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         }
     };
     stamp(0);
+    // programmatic dependent launch (see the team kernel below): no-ops unless the host launched with stream serialisation
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
     constexpr int NI = Cfg::NI, KC = Cfg::KC, NBUF = Cfg::NBUF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // swizzle atoms
@@ -330,6 +333,8 @@ gemm_skinny_xreg_f64_kernel(const __grid_constant__ CUtensorMap mapA, const doub
                             int64_t ldd, const double* __restrict__ Cin, int64_t ldc)
 {
     constexpr int KSTEPS = Cfg::KSTEPS, NG = Cfg::NG, NBUF = Cfg::NBUF;
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // programmatic dependent launch, as in the team kernel below
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // swizzle atoms
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
