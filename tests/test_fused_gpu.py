@@ -104,3 +104,28 @@ def test_fused_forms_empty_contraction(jb):
     jb.gemm_x_plus_c_(dD, to_dev(np.zeros((M, 0), order="F")), to_dev(np.zeros((0, N), order="F")), to_dev(np.zeros((0, N), order="F")))
     torch.cuda.synchronize()
     assert (to_host(dD) == 0).all()
+
+
+@pytest.mark.parametrize("shape", [(20000, 64, 64), (17001, 64, 40), (30000, 72, 48)], ids=lambda s: "x".join(map(str, s)))
+def test_fused_forms_on_the_tall_skinny_kernels(jb, shape):
+    """D = A*X + C and D = A*(X + C) on shapes AUTO gives to the tall-skinny kernels (team kernel for K = 64, the shared-memory
+    variant for K = 72): C is a separate matrix with its own leading dimension, read as the start of every chain; bit-identical."""
+    import torch
+
+    M, K, N = shape
+    assert "skinny" in jb.plan(M + (M & 1), K, N)["kernel"]
+    A, X = randn_f((M, K), np.float64, SEED_A, ld=M + (M & 1)), randn_f((K, N), np.float64, SEED_X)
+    Ad = np.asfortranarray(A)
+    C = randn_f((M, N), np.float64, 11, ld=M + 4 - (M & 1) * 0 + (M & 1))
+    dA, dX, dC = to_dev(A), to_dev(X), to_dev(C)
+    dD = to_dev(nan_f((M, N), np.float64, ld=M + 2 + (M & 1)))
+    jb.gemm_plus_c_(dD, dA, dX, dC)
+    torch.cuda.synchronize()
+    assert bits_equal(to_host(dD), oracle.oracle_gemm(Ad, X, np.asfortranarray(C).copy(order="F"), accumulate=True))
+    assert bits_equal(to_host(dC), np.asfortranarray(C))
+    C2 = randn_f((K, N), np.float64, 12)
+    dC2 = to_dev(C2)
+    dD2 = to_dev(nan_f((M, N), np.float64))
+    jb.gemm_x_plus_c_(dD2, dA, dX, dC2)
+    torch.cuda.synchronize()
+    assert bits_equal(to_host(dD2), oracle.oracle_gemm(Ad, np.asfortranarray(X + C2)))
