@@ -239,6 +239,29 @@ static cudaError_t attr_dmma()
     return cudaSuccess;
 }
 
+// Launch with programmatic stream serialisation (the kernel calls griddepcontrol.wait before its first global access): the next
+// such launch on the stream is scheduled while this one runs.  JBLAS_B200_NO_PDL=1 launches plainly (A/B measurements).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t s, Args... args)
+{
+    static int no_pdl = -1;
+    if (no_pdl < 0) {
+        const char* e = getenv("JBLAS_B200_NO_PDL");
+        no_pdl = (e && atoi(e)) ? 1 : 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- TMA tensor maps (driver entry point resolved at run time: the library must load without libcuda.so.1) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -329,8 +352,10 @@ static int launch_dmma_tma(void* D, const void* A, const void* X, int M, int N, 
         static_tiles = (e && atoi(e)) ? 1 : 0;
     }
     int* ctr = static_tiles ? nullptr : tile_counter_for(s);
-    gemm_dmma_tma_kernel<Cfg, ACC><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(mapA, mapX, (double*)D, M, N, K, ldd, tiles_m, tiles_n,
-                                                                           group_m, pa, px, ctr, (const double*)Cin, ldc);
+    // programmatic dependent launch: the next product of the stream is scheduled while this one runs (1.7 us per call on small
+    // shapes); the kernel waits for all earlier work before its first global access (counter, TMA, C)
+    CUDA_TRY(launch_pdl(gemm_dmma_tma_kernel<Cfg, ACC, false, false>, grid, Cfg::THREADS, Cfg::SMEM, s, mapA, mapX, (double*)D, M, N, K, ldd, tiles_m, tiles_n,
+                        group_m, pa, px, ctr, (const double*)Cin, ldc, 1, (int64_t)0, (const double*)nullptr, (const double*)nullptr, (int64_t)0, (int64_t)0));
     return 0;
 }
 template <typename Cfg, bool ACC>
@@ -361,9 +386,8 @@ static int launch_dmma_tma_ragged(void* D, const void* A, const void* X, int M, 
     static const CUtensorMap none = {};
     int grid = tiles_m * tiles_n;
     if (grid > g_ctx.num_sms * Cfg::MIN_BLOCKS) grid = g_ctx.num_sms * Cfg::MIN_BLOCKS;
-    gemm_dmma_tma_kernel<Cfg, ACC, false, true><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(none, none, (double*)D, M, N, K, ldd, tiles_m, tiles_n, group_m,
-                                                                                        kL2EvictNormal, kL2EvictNormal, nullptr, (const double*)Cin, ldc, 1, 0,
-                                                                                        (const double*)A, (const double*)X, lda, ldx);
+    CUDA_TRY(launch_pdl(gemm_dmma_tma_kernel<Cfg, ACC, false, true>, grid, Cfg::THREADS, Cfg::SMEM, s, none, none, (double*)D, M, N, K, ldd, tiles_m, tiles_n, group_m,
+                        kL2EvictNormal, kL2EvictNormal, (int*)nullptr, (const double*)Cin, ldc, 1, (int64_t)0, (const double*)A, (const double*)X, lda, ldx));
     return 0;
 }
 template <typename Cfg>
@@ -375,29 +399,6 @@ static cudaError_t attr_dmma_tma_ragged()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_dmma_tma_kernel<Cfg, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     return e;
 }
-// Launch with programmatic stream serialisation (the kernel calls griddepcontrol.wait before its first global access): the next
-// such launch on the stream is scheduled while this one runs.  JBLAS_B200_NO_PDL=1 launches plainly (A/B measurements).
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t s, Args... args)
-{
-    static int no_pdl = -1;
-    if (no_pdl < 0) {
-        const char* e = getenv("JBLAS_B200_NO_PDL");
-        no_pdl = (e && atoi(e)) ? 1 : 0;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 // General tiled tensor map (rank 3 or 4, Float64) with a small per-thread cache, as make_tmap_2d.
 static int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstride_bytes, const cuuint32_t* box,
                         CUtensorMapSwizzle swizzle)

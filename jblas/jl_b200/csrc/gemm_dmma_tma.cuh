@@ -199,6 +199,11 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     volatile int* stage_tile = reinterpret_cast<volatile int*>(empty + STAGES);  // tile a stage belongs to; -1 = no more work
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Programmatic dependent launch (host: launch_pdl).  launch_dependents lets the NEXT kernel of the stream be scheduled while
+    // this one runs (its CTAs take the SMs as ours retire and do their barrier set-up early); wait holds THIS kernel until every
+    // earlier kernel of the stream has completed and flushed -- before the first global access (tile counter, TMA, C).  Both
+    // are no-ops for plain launches.
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
@@ -208,6 +213,7 @@ gemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         mbar_fence_init();
     }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
     const int tiles_per_product = tiles_m * tiles_n;
     const int num_tiles = tiles_per_product * (BATCHED ? batch : 1);
