@@ -142,6 +142,29 @@ static int* tile_counter_for(cudaStream_t s)
     return c.tile_ctr + 2 * it->second;
 }
 
+// Launch with programmatic stream serialisation (the kernel calls griddepcontrol.wait before its first global access): the next
+// such launch on the stream is scheduled while this one runs.  JBLAS_B200_NO_PDL=1 launches plainly (A/B measurements).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t s, Args... args)
+{
+    static int no_pdl = -1;
+    if (no_pdl < 0) {
+        const char* e = getenv("JBLAS_B200_NO_PDL");
+        no_pdl = (e && atoi(e)) ? 1 : 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // kernel registry
 // ---------------------------------------------------------------------------------------------------------
@@ -182,8 +205,8 @@ template <typename T, typename Cfg, bool ALIGNED, bool ACC>
 static int launch_simt(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
                        int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
 {
-    gemm_simt_kernel<T, Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
-        (T*)D, (const T*)A, (const T*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m, (const T*)Cin, ldc);
+    CUDA_TRY(launch_pdl(gemm_simt_kernel<T, Cfg, ALIGNED, ACC>, tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s, (T*)D, (const T*)A, (const T*)X, M, N, K, ldd, lda, ldx,
+                        tiles_m, tiles_n, group_m, (const T*)Cin, ldc));
     return 0;
 }
 template <typename T, typename Cfg>
@@ -202,8 +225,8 @@ template <typename Cfg, bool ALIGNED, bool ACC>
 static int launch_simt_f32x2(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
                              int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
 {
-    gemm_simt_f32x2_kernel<Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
-        (float*)D, (const float*)A, (const float*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m, (const float*)Cin, ldc);
+    CUDA_TRY(launch_pdl(gemm_simt_f32x2_kernel<Cfg, ALIGNED, ACC>, tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s, (float*)D, (const float*)A, (const float*)X, M, N, K,
+                        ldd, lda, ldx, tiles_m, tiles_n, group_m, (const float*)Cin, ldc));
     return 0;
 }
 template <typename Cfg>
@@ -222,8 +245,8 @@ template <typename Cfg, bool ALIGNED, bool ACC>
 static int launch_dmma(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx,
                        int tiles_m, int tiles_n, int group_m, cudaStream_t s, const void* Cin, int64_t ldc)
 {
-    gemm_dmma_kernel<Cfg, ALIGNED, ACC><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s>>>(
-        (double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, tiles_m, tiles_n, group_m, (const double*)Cin, ldc);
+    CUDA_TRY(launch_pdl(gemm_dmma_kernel<Cfg, ALIGNED, ACC>, tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM, s, (double*)D, (const double*)A, (const double*)X, M, N, K,
+                        ldd, lda, ldx, tiles_m, tiles_n, group_m, (const double*)Cin, ldc));
     return 0;
 }
 template <typename Cfg>
@@ -237,29 +260,6 @@ static cudaError_t attr_dmma()
     SET(false, false) SET(false, true) SET(true, false) SET(true, true)
 #undef SET
     return cudaSuccess;
-}
-
-// Launch with programmatic stream serialisation (the kernel calls griddepcontrol.wait before its first global access): the next
-// such launch on the stream is scheduled while this one runs.  JBLAS_B200_NO_PDL=1 launches plainly (A/B measurements).
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t s, Args... args)
-{
-    static int no_pdl = -1;
-    if (no_pdl < 0) {
-        const char* e = getenv("JBLAS_B200_NO_PDL");
-        no_pdl = (e && atoi(e)) ? 1 : 0;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- TMA tensor maps (driver entry point resolved at run time: the library must load without libcuda.so.1) ----

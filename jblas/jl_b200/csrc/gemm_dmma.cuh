@@ -53,6 +53,9 @@ gemm_dmma_kernel(double* D, const double* __restrict__ A, const double* __restri
 {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
     constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB, THREADS = Cfg::THREADS;
+    // programmatic dependent launch (capi.cu: launch_pdl): no-ops for plain launches; the wait precedes every global access
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
 

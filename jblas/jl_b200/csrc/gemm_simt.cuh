@@ -46,6 +46,9 @@ gemm_simt_kernel(T* D, const T* __restrict__ A, const T* __restrict__ X, int M, 
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, VEC = Cfg::VEC, NI = Cfg::NI;
     constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB, THREADS = Cfg::THREADS;
     using V = Vec16<T, VEC>;
+    // programmatic dependent launch (capi.cu: launch_pdl): no-ops for plain launches; the wait precedes every global access
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
 

@@ -60,6 +60,9 @@ gemm_simt_f32x2_kernel(float* D, const float* __restrict__ A, const float* __res
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
     constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB, THREADS = Cfg::THREADS;
     static_assert(Cfg::VEC == 4, "Float32 only");
+    // programmatic dependent launch (capi.cu: launch_pdl): no-ops for plain launches; the wait precedes every global access
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* smem = reinterpret_cast<float*>(smem_raw);
 
