@@ -1,6 +1,15 @@
 // gemm_skinny.cuh -- tall-skinny FP64 product D(M x N) = A(M x K) * X(K x N) with N <= 64 and a short K:
-// X stays RESIDENT in shared memory, A is streamed from HBM exactly once, D is written exactly once.
+// X stays RESIDENT on the SM, A is streamed from HBM exactly once, D is written exactly once.
 //
+// THREE kernels, in the order they were built (DESIGN.md s4 "Tall-skinny" has the measurements that led from one to the next):
+//   1. gemm_skinny_f64_kernel       X in shared memory, warp-private TMA boxes, 16 x 64 items        (N <= 64, K <= 128, K % 8 == 0)
+//   2. gemm_skinny_xreg_f64_kernel  X fragments in REGISTERS, warp-private boxes, 16 x 32 items     (K = 32 / 64; explicit selector)
+//   3. gemm_skinny_team_f64_kernel  X fragments in registers, ONE box per row block shared by a team of four quarter-column
+//                                   warps, 16 warps per SM                                          (K = 32 / 64; AUTO for N > 32)
+// All three chain every element in ascending k from -0.0 (or C) with 4 k per DMMA: bit-identical to the reference chain on B200;
+// all three are launched with programmatic stream serialisation (griddepcontrol.wait precedes their first global access).
+//
+// ---- kernel 1 ----
 // Regime (BASELINE configs[3], 65536 x 64 x 64): 8 flop per byte -- the FP64 pipe (14.4 us) and HBM (10.3 us) bind almost
 // together, so neither may idle.  The reference's analogue is fastmul!'s thin panel (src/kernels.jl:202-208): the whole X
 // is small, A is a tall stack of row blocks.  A tile kernel is the wrong shape for it (K = 64 is two pipeline stages; every
