@@ -597,3 +597,28 @@ def test_mrandn_is_seeded_standard_normal(jb):
     assert torch.equal(longer[:, :777], a)
     odd = jb.mrandn(3, 5)
     assert torch.isfinite(odd).all()
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (256, 256), (1023, 777), (16384, 64), (20001, 48), (130, 70)], ids=lambda s: "x".join(map(str, s)))
+def test_back_to_back_dependent_products_under_programmatic_dependent_launch(jb, shape):
+    """Every kernel family is launched with programmatic stream serialisation: the NEXT launch of a stream is scheduled while
+    the current one runs and must not touch global memory before griddepcontrol.wait.  A chain of dependent products issued
+    back to back with no synchronisation -- D1 = A*X1, D2 = D1*X2, D3 = D2*X3, ... where each launch READS what the previous
+    one is still writing if the wait were misplaced -- must reproduce, stage by stage and bit for bit, the oracle applied to
+    the GPU's own previous stage.  Repeated so that a race would have many chances."""
+    import torch
+
+    M, N = shape
+    steps = 5
+    A = randn_f((M, N), seed=SEED_A, ld=M + (M & 1))
+    Xs = [randn_f((N, N), seed=SEED_X + i) * (1.0 / np.sqrt(N)) for i in range(steps)]
+    dXs = [to_dev(np.asfortranarray(x)) for x in Xs]
+    for rep in range(6):
+        stages = [to_dev(A)] + [to_dev(nan_f((M, N), ld=M + (M & 1))) for _ in range(steps)]
+        for i in range(steps):  # no synchronisation in between
+            jb.gemm_(stages[i + 1], stages[i], dXs[i])
+        torch.cuda.synchronize()
+        host = [to_host(t) for t in stages]
+        for i in range(steps):
+            want = oracle.oracle_gemm(np.asfortranarray(host[i]), np.asfortranarray(Xs[i]))
+            assert bits_equal(host[i + 1], want), (shape, rep, i, jb.plan(M, N, N, lda=M + (M & 1))["kernel"])
