@@ -505,8 +505,10 @@ static cudaError_t attr_skinny_xreg()
 // X in registers, boxes shared by a team of four quarter-column warps (gemm_skinny.cuh, third kernel): K = 64 or 32 exactly.
 // Launched with programmatic stream serialisation: a following launch of the same kind is scheduled while this one runs and
 // waits (griddepcontrol.wait) before its first global access -- 1.7 us less per call in back-to-back streams of products.
-using SKT_k64 = SkinnyTeamCfg<16, 16, 3, 2>;
-using SKT_k32 = SkinnyTeamCfg<8, 16, 3, 2>;
+//                                    KSTEPS WARPS NBUF NG  BN      (team = BN / (8 NG) warps share one box)
+template <int KS> using SKT_n64 = SkinnyTeamCfg<KS, 16, 3, 2, 64>;  // 32 < N <= 64: four quarter-column warps
+template <int KS> using SKT_n16 = SkinnyTeamCfg<KS, 16, 3, 1, 16>;  //      N <= 16: two warps of one column tile (262144 x 16 x 32: 18.0 vs 24.4 us,
+                                                                     //                5.6 TB/s of algorithmic traffic)
 template <typename Cfg, bool ACC>
 static int launch_skinny_team_cfg(double* D, const double* A, const double* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx, cudaStream_t s,
                                   const double* Cin, int64_t ldc)
@@ -522,22 +524,35 @@ static int launch_skinny_team_cfg(double* D, const double* A, const double* X, i
     CUDA_TRY(launch_pdl(gemm_skinny_team_f64_kernel<Cfg, ACC>, grid, Cfg::THREADS, Cfg::SMEM, s, mapA, X, ldx, D, M, N, ldd, Cin, ldc));
     return 0;
 }
+template <int KS, bool ACC>
+static int launch_skinny_team_k(double* D, const double* A, const double* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx, cudaStream_t s,
+                                const double* Cin, int64_t ldc)
+{
+    if (N > 16) return launch_skinny_team_cfg<SKT_n64<KS>, ACC>(D, A, X, M, N, K, ldd, lda, ldx, s, Cin, ldc);  // (16 < N <= 32 when forced: two members idle)
+    return launch_skinny_team_cfg<SKT_n16<KS>, ACC>(D, A, X, M, N, K, ldd, lda, ldx, s, Cin, ldc);
+}
 template <bool ACC>
 static int launch_skinny_team(void* D, const void* A, const void* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx, int, int, int, cudaStream_t s,
                               const void* Cin, int64_t ldc)
 {
     if (!skinny_xreg_shape_ok(M, N, K))
         return fail(JBLAS_B200_EUNSUPPORTED, "the team tall-skinny kernel takes N <= %d and K = 32 or 64 (got N=%d K=%d)", kSkinnyMaxN, N, K);
-    if (K == 32) return launch_skinny_team_cfg<SKT_k32, ACC>((double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, s, (const double*)Cin, ldc);
-    return launch_skinny_team_cfg<SKT_k64, ACC>((double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, s, (const double*)Cin, ldc);
+    if (K == 32) return launch_skinny_team_k<8, ACC>((double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, s, (const double*)Cin, ldc);
+    return launch_skinny_team_k<16, ACC>((double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, s, (const double*)Cin, ldc);
+}
+template <typename Cfg>
+static cudaError_t attr_skinny_team_cfg()
+{
+    cudaError_t e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    return e;
 }
 static cudaError_t attr_skinny_team()
 {
-    cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<SKT_k64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKT_k64::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<SKT_k64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKT_k64::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<SKT_k32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKT_k32::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_skinny_team_f64_kernel<SKT_k32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKT_k32::SMEM);
+    cudaError_t e = attr_skinny_team_cfg<SKT_n64<16>>();
+    if (e == cudaSuccess) e = attr_skinny_team_cfg<SKT_n64<8>>();
+    if (e == cudaSuccess) e = attr_skinny_team_cfg<SKT_n16<16>>();
+    if (e == cudaSuccess) e = attr_skinny_team_cfg<SKT_n16<8>>();
     return e;
 }
 static cudaError_t attr_skinny()
@@ -766,7 +781,7 @@ static const KernelInfo g_kernels[] = {
               {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny<false>, launch_skinny<true>}}, attr_skinny, nullptr},
     /* 31 */ {"dmma_skinny_f64_16x32_xreg_w8", JBLAS_B200_DT_F64, FAM_DMMA, 16, 32, 64, 2, SKR_k64::THREADS, SKR_k64::SMEM, 1.0f, true, true, 1,
               {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny_xreg<false>, launch_skinny_xreg<true>}}, attr_skinny_xreg, nullptr},
-    /* 32 */ {"dmma_skinny_f64_16x16_xreg_team_w16", JBLAS_B200_DT_F64, FAM_DMMA, 16, 64, 64, 3, SKT_k64::THREADS, SKT_k64::SMEM, 1.0f, true, true, 1,
+    /* 32 */ {"dmma_skinny_f64_16x16_xreg_team_w16", JBLAS_B200_DT_F64, FAM_DMMA, 16, 64, 64, 3, SKT_n64<16>::THREADS, SKT_n64<16>::SMEM, 1.0f, true, true, 1,
               {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny_team<false>, launch_skinny_team<true>}}, attr_skinny_team, nullptr},
 };
 static constexpr int NUM_KERNELS = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
@@ -824,11 +839,12 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
     // (gemm_skinny.cuh).  Measured against the best tile kernel on cold operands: 23.3 vs 24.9 us at 65536 x 64 x 64.
     // K = 64 or 32: the variant that keeps the X fragments in registers (22.6 us; tensor pipe 90 % in the steady state).
     if (explicit_idx < 0 && dtype == JBLAS_B200_DT_F64 && family == FAM_DMMA && out->aligned && M >= 16384) {
-        // measured (profiles/r2_skinny_compare.txt): with both column halves in use (N > 32) the register variants win, and the
-        // team kernel (one box per row block, four quarter-column warps, 16 warps per SM) is the one that stays at the algorithmic
-        // DRAM traffic for any M (10^6 rows: 239 us against 293 for private boxes and 258 for the shared-memory variant);
-        // for N <= 32 the shared-memory variant with its 4-tile configuration is faster (14.9 vs 16.4 us at 65536 x 32 x 64)
-        if (skinny_xreg_shape_ok(M, N, K) && N > 32) best = kSkinnyTeamKernel;
+        // measured (profiles/r2_skinny_compare.txt): the team kernel (X fragments in registers, one box per row block shared by the
+        // warps that cover its columns, 16 warps per SM) wins for 32 < N <= 64 (four quarter-column warps) and for N <= 16 (two
+        // one-tile warps: 262144 x 16 x 32 in 18.0 us against 22.2), and it stays at the algorithmic DRAM traffic for any M (10^6
+        // rows: 248 us against 293 for private boxes, 253 for the shared-memory variant); for 16 < N <= 32 the shared-memory variant's
+        // 4-tile configuration is as fast or faster at every M (65536 x 32 x 64: 13.0 us against 12.7 / 14.9 for the team widths tried)
+        if (skinny_xreg_shape_ok(M, N, K) && (N > 32 || N <= 16)) best = kSkinnyTeamKernel;
         else if (skinny_shape_ok(M, N, K)) best = kSkinnyKernel;
     }
     const bool by_shape_rule = best >= 0;

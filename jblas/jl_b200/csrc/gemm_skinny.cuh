@@ -497,10 +497,10 @@ gemm_skinny_xreg_f64_kernel(const __grid_constant__ CUtensorMap mapA, const doub
 // `empty` phase has completed, and it asks one item later than it could, so that it practically never waits for a team mate.
 // With quarters a warp needs ~120 registers: 16 warps per SM (four per sub-partition) hide each other's non-DMMA instructions.
 // =====================================================================================================================
-template <int KSTEPS_, int WARPS_, int NBUF_ = 3, int NG_ = 2>
+template <int KSTEPS_, int WARPS_, int NBUF_ = 3, int NG_ = 2, int BN_ = 64>
 struct SkinnyTeamCfg {
     static constexpr int KSTEPS = KSTEPS_, K = 4 * KSTEPS_, WARPS = WARPS_, THREADS = WARPS_ * 32, NBUF = NBUF_, NG = NG_;
-    static constexpr int TEAM = 64 / (8 * NG_), TEAMS = WARPS_ / TEAM, BN = 64;
+    static constexpr int TEAM = BN_ / (8 * NG_), TEAMS = WARPS_ / TEAM, BN = BN_;  // BN = 32: teams of two warps for N <= 32
     static constexpr int BOX_BYTES = 16 * K * 8;
     static_assert(WARPS_ % TEAM == 0 && NBUF_ >= 2, "whole teams, at least two boxes per team");
     static_assert(KSTEPS_ % 2 == 0 && BOX_BYTES % 1024 == 0, "a box is a whole number of swizzle atoms");
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 gemm_skinny_team_f64_kernel(const __grid_constant__ CUtensorMap mapA, const double* __restrict__ X, int64_t ldx, double* __restrict__ D, int M, int N,
                             int64_t ldd, const double* __restrict__ Cin, int64_t ldc)
 {
-    constexpr int KSTEPS = Cfg::KSTEPS, NG = Cfg::NG, NBUF = Cfg::NBUF, TEAM = Cfg::TEAM, GW = 8 * NG;
+    constexpr int KSTEPS = Cfg::KSTEPS, NG = Cfg::NG, NBUF = Cfg::NBUF, TEAM = Cfg::TEAM, GW = 8 * NG;  // GW columns per member, TEAM GW = Cfg::BN >= N
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // swizzle atoms
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

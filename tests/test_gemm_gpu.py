@@ -496,7 +496,7 @@ def test_tall_skinny_kernel_limits(jb):
     # AUTO: only tall shapes with a short contraction take it; everything else stays on the tile kernels
     assert jb.plan(65536, 64, 64)["kernel"] == SKINNY_TEAM and jb.plan(300000, 32, 40)["kernel"] == SKINNY_TEAM and jb.plan(1 << 20, 64, 64)["kernel"] == SKINNY_TEAM
     assert jb.plan(300000, 128, 40)["kernel"] == SKINNY and jb.plan(65536, 72, 48)["kernel"] == SKINNY
-    assert jb.plan(65536, 64, 32)["kernel"] == SKINNY  # one column half: the shared-memory variant's 4-tile configuration
+    assert jb.plan(65536, 64, 32)["kernel"] == SKINNY and jb.plan(262144, 32, 16)["kernel"] == SKINNY_TEAM  # 16 < N <= 32: shared-memory variant
     assert jb.plan(4096, 64, 64)["kernel"] != SKINNY and jb.plan(65536, 256, 64)["kernel"] != SKINNY and jb.plan(65536, 64, 128)["kernel"] != SKINNY
     assert jb.plan(65535, 64, 64)["kernel"] != SKINNY  # odd leading dimension: the ragged producers of the tile kernels
 

@@ -36,7 +36,7 @@ def timeit(fn, bufs, reps=200):
 
 
 for (M, N, K) in [(65536, 64, 64), (16384, 64, 64), (32768, 64, 64), (131072, 64, 64), (300000, 64, 64), (1000000, 64, 64), (65536, 32, 64), (65536, 64, 128),
-                  (65536, 48, 72), (65536, 48, 64), (262144, 16, 32), (131072, 64, 32)]:
+                  (65536, 48, 72), (65536, 48, 64), (262144, 16, 32), (131072, 64, 32), (300000, 32, 64), (262144, 16, 64), (65536, 8, 64)]:
     nbytes = (M * K + K * N + M * N) * 8
     sets = max(2, min(12, -(-400_000_000 // nbytes)))
     bufs = [(jb.empty_colmajor(M, N, "float64"), jb.mrandn(M, K, "float64", seed=2 * i + 1), jb.mrandn(K, N, "float64", seed=2 * i + 2)) for i in range(sets)]

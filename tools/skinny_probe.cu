@@ -566,6 +566,11 @@ int main(int argc, char** argv)
     if (only == -5 || only == 129) run_xreg<SkinnyTeamCfg<24, 12, 3, 2>, true>("team k96 w12 quarters nbuf3", M, N, K, As, X, Ds, Dref, sms);
     if (only == -5 || only == 130) run_xreg<SkinnyTeamCfg<24, 8, 3, 2>, true>("team k96 w8 quarters nbuf3", M, N, K, As, X, Ds, Dref, sms);
     if (only == -5 || only == 131) run_xreg<SkinnyTeamCfg<4, 16, 3, 2>, true>("team k16 w16 quarters nbuf3", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 132) run_xreg<SkinnyTeamCfg<16, 16, 3, 2, 32>, true>("team k64 w16 quarters BN32", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 133) run_xreg<SkinnyTeamCfg<16, 16, 3, 1, 32>, true>("team k64 w16 eighths BN32", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 134) run_xreg<SkinnyTeamCfg<8, 16, 3, 2, 32>, true>("team k32 w16 quarters BN32", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 135) run_xreg<SkinnyTeamCfg<16, 16, 3, 1, 16>, true>("team k64 w16 eighths BN16", M, N, K, As, X, Ds, Dref, sms);
+    if (only == -5 || only == 136) run_xreg<SkinnyTeamCfg<8, 16, 3, 1, 16>, true>("team k32 w16 eighths BN16", M, N, K, As, X, Ds, Dref, sms);
     if (only == -5 || only >= 100) return 0;
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 12, 32, 3>>("w12 kc32 stagger+late", M, N, K, As, X, Ds, Dref, sms);
     if (only < 0 || only == idx++) run<SkinnyCfg<8, 8, 64, 3>>("w8 kc64 stagger+late", M, N, K, As, X, Ds, Dref, sms);
