@@ -466,8 +466,8 @@ static int launch_skinny(void* D, const void* A, const void* X, int M, int N, in
     return launch_skinny_cfg<SK_n64, ACC>((double*)D, (const double*)A, (const double*)X, M, N, K, ldd, lda, ldx, s, (const double*)Cin, ldc);
 }
 // X in registers (gemm_skinny.cuh, second kernel): K = 64 or 32 exactly
-using SKR_k64 = SkinnyRegCfg<16, 8, 2>;   // 212 registers: 8 warps
-using SKR_k32 = SkinnyRegCfg<8, 12, 2>;   // 142 registers: 12 warps
+using SKR_k64 = SkinnyRegCfg<16, 8, 3, 2>;   // column quarters (16 columns per warp), private boxes, three per warp
+using SKR_k32 = SkinnyRegCfg<8, 12, 2, 2>;
 static bool skinny_xreg_shape_ok(int64_t M, int64_t N, int64_t K) { return M >= 1 && N >= 1 && N <= kSkinnyMaxN && (K == 64 || K == 32); }
 template <typename Cfg, bool ACC>
 static int launch_skinny_xreg_cfg(double* D, const double* A, const double* X, int M, int N, int K, int64_t ldd, int64_t lda, int64_t ldx, cudaStream_t s,
@@ -478,7 +478,8 @@ static int launch_skinny_xreg_cfg(double* D, const double* A, const double* X, i
     const cuuint64_t gstr[3] = {(cuuint64_t)(4 * lda * 8), (cuuint64_t)(lda * 8), (cuuint64_t)(8 * lda * 8)};
     const cuuint32_t box[4] = {16, 2, 4, (cuuint32_t)(K / 8)};
     if (int rc = make_tmap_nd(&mapA, A, 4, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    const int items = ((M + 15) / 16) * (N > 32 ? 2 : 1);
+    const int groups = (N + 8 * Cfg::NG - 1) / (8 * Cfg::NG);  // column groups in use; every warp owns one of them
+    const int items = ((M + 15) / 16) * groups;
     int grid = (items + Cfg::WARPS - 1) / Cfg::WARPS;
     if (grid > g_ctx.num_sms) grid = g_ctx.num_sms;
     CUDA_TRY(launch_pdl(gemm_skinny_xreg_f64_kernel<Cfg, ACC>, grid, Cfg::THREADS, Cfg::SMEM, s, mapA, X, ldx, D, M, N, ldd, Cin, ldc));
@@ -779,7 +780,7 @@ static const KernelInfo g_kernels[] = {
     /* 29 */ TF32X3_PAIR_ENTRY("tf32x3_tcgen05_2cta_f32_256x256x32_s3", X3_PAIR, 1.11f),  // 8192^3: 270.8 vs 243.7 TFLOP/s, 16384^3: 239 vs 214 (same box, incl. the split)
     /* 30 */ {"dmma_skinny_f64_16x64_xres_w12", JBLAS_B200_DT_F64, FAM_DMMA, 16, 64, 32, 2, SK_n64::THREADS, SK_n64::smem(64), 1.0f, true, true, 1,
               {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny<false>, launch_skinny<true>}}, attr_skinny, nullptr},
-    /* 31 */ {"dmma_skinny_f64_16x32_xreg_w8", JBLAS_B200_DT_F64, FAM_DMMA, 16, 32, 64, 2, SKR_k64::THREADS, SKR_k64::SMEM, 1.0f, true, true, 1,
+    /* 31 */ {"dmma_skinny_f64_16x16_xreg_w8", JBLAS_B200_DT_F64, FAM_DMMA, 16, 16, 64, 3, SKR_k64::THREADS, SKR_k64::SMEM, 1.0f, true, true, 1,
               {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny_xreg<false>, launch_skinny_xreg<true>}}, attr_skinny_xreg, nullptr},
     /* 32 */ {"dmma_skinny_f64_16x16_xreg_team_w16", JBLAS_B200_DT_F64, FAM_DMMA, 16, 64, 64, 3, SKT_n64<16>::THREADS, SKT_n64<16>::SMEM, 1.0f, true, true, 1,
               {{launch_needs_alignment, launch_needs_alignment}, {launch_skinny_team<false>, launch_skinny_team<true>}}, attr_skinny_team, nullptr},
@@ -844,7 +845,11 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
         // one-tile warps: 262144 x 16 x 32 in 18.0 us against 22.2), and it stays at the algorithmic DRAM traffic for any M (10^6
         // rows: 248 us against 293 for private boxes, 253 for the shared-memory variant); for 16 < N <= 32 the shared-memory variant's
         // 4-tile configuration is as fast or faster at every M (65536 x 32 x 64: 13.0 us against 12.7 / 14.9 for the team widths tried)
-        if (skinny_xreg_shape_ok(M, N, K) && (N > 32 || N <= 16)) best = kSkinnyTeamKernel;
+        // While A fits in L2 (48 MB here) the private-box variant is ~1 us faster: the four quarter-column warps of a row block
+        // re-fetch its box from L2, not from DRAM, and need no hand-shake (65536 x 64 x 64: 19.9 against 20.8 us, 32768 rows: 11.7
+        // against 12.8); beyond that the re-fetches go to DRAM (10^6 rows: 512 us) and the team kernel takes over.
+        if (skinny_xreg_shape_ok(M, N, K) && N > 32 && K == 64 && (double)M * (double)K * 8.0 <= 48.0e6) best = kSkinnyXregKernel;  // (K = 32: team 23.8 vs 24.9 us)
+        else if (skinny_xreg_shape_ok(M, N, K) && (N > 32 || N <= 16)) best = kSkinnyTeamKernel;
         else if (skinny_shape_ok(M, N, K)) best = kSkinnyKernel;
     }
     const bool by_shape_rule = best >= 0;

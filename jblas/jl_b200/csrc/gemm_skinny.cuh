@@ -3,7 +3,7 @@
 //
 // THREE kernels, in the order they were built (DESIGN.md s4 "Tall-skinny" has the measurements that led from one to the next):
 //   1. gemm_skinny_f64_kernel       X in shared memory, warp-private TMA boxes, 16 x 64 items        (N <= 64, K <= 128, K % 8 == 0)
-//   2. gemm_skinny_xreg_f64_kernel  X fragments in REGISTERS, warp-private boxes, 16 x 32 items     (K = 32 / 64; explicit selector)
+//   2. gemm_skinny_xreg_f64_kernel  X fragments in REGISTERS, warp-private boxes, 16 x 16 items     (K = 32 / 64; AUTO while A fits in L2)
 //   3. gemm_skinny_team_f64_kernel  X fragments in registers, ONE box per row block shared by a team of four quarter-column
 //                                   warps, 16 warps per SM                                          (K = 32 / 64; AUTO for N > 32)
 // All three chain every element in ascending k from -0.0 (or C) with 4 k per DMMA: bit-identical to the reference chain on B200;
@@ -357,6 +357,7 @@ gemm_skinny_xreg_f64_kernel(const __grid_constant__ CUtensorMap mapA, const doub
     const int half = warp % halves;
     const int hw = (warp / halves) * gridDim.x + blockIdx.x;
     const int HW = (Cfg::WARPS / halves) * gridDim.x;
+    if (warp >= halves * (Cfg::WARPS / halves)) return;  // three column groups on eight warps: the two surplus warps sit the launch out
     const int nblocks = (M + 15) >> 4;
 
     if (lane == 0) {

@@ -438,18 +438,18 @@ def test_config_tall_skinny_65536x64x64(jb):
     A, X = randn_f((M, K)), randn_f((K, N), seed=SEED_X)
     want = oracle.oracle_gemm(A, X)
     assert bits_equal(_run_dev(jb, A, X, jb.F64_SIMT), want)
-    assert jb.plan(M, K, N)["kernel"] == SKINNY_TEAM  # AUTO: the dedicated tall-skinny kernel (X in registers, A streamed once)
+    assert jb.plan(M, K, N)["kernel"] == SKINNY_XREG  # AUTO: the dedicated tall-skinny kernel (X in registers, A streamed once; A fits in L2: private boxes)
     assert bits_equal(_run_dev(jb, A, X, jb.F64_AUTO), want)  # DMMA chains like the reference on B200: every bit
 
 
 SKINNY = "dmma_skinny_f64_16x64_xres_w12"
-SKINNY_XREG = "dmma_skinny_f64_16x32_xreg_w8"
+SKINNY_XREG = "dmma_skinny_f64_16x16_xreg_w8"
 SKINNY_TEAM = "dmma_skinny_f64_16x16_xreg_team_w16"
 
 
 @pytest.mark.parametrize("shape", [(65536, 64, 64), (20000, 64, 48), (16385, 32, 33), (100, 64, 64), (5000, 32, 17), (3000, 64, 32), (1, 32, 1),
                                    (40000, 32, 64), (16 * 592 * 3 + 21, 64, 64)], ids=lambda s: "x".join(map(str, s)))
-@pytest.mark.parametrize("kernel_name", ["dmma_skinny_f64_16x32_xreg_w8", "dmma_skinny_f64_16x16_xreg_team_w16"])
+@pytest.mark.parametrize("kernel_name", ["dmma_skinny_f64_16x16_xreg_w8", "dmma_skinny_f64_16x16_xreg_team_w16"])
 def test_tall_skinny_xreg_kernel_bit_identical(jb, shape, kernel_name):
     """The X-in-registers variants (K = 64 or 32; private boxes per column half, or one box per row block shared by a team of four
     quarter-column warps and launched with programmatic stream serialisation) forced on shapes around their limits: N < 64 (zero X fragments, guarded stores),
@@ -494,7 +494,7 @@ def test_tall_skinny_kernel_limits(jb):
     with pytest.raises(jb.JblasB200Error):
         _run_dev(jb, A, X, sel)
     # AUTO: only tall shapes with a short contraction take it; everything else stays on the tile kernels
-    assert jb.plan(65536, 64, 64)["kernel"] == SKINNY_TEAM and jb.plan(300000, 32, 40)["kernel"] == SKINNY_TEAM and jb.plan(1 << 20, 64, 64)["kernel"] == SKINNY_TEAM
+    assert jb.plan(65536, 64, 64)["kernel"] == SKINNY_XREG and jb.plan(300000, 32, 40)["kernel"] == SKINNY_TEAM and jb.plan(1 << 20, 64, 64)["kernel"] == SKINNY_TEAM
     assert jb.plan(300000, 128, 40)["kernel"] == SKINNY and jb.plan(65536, 72, 48)["kernel"] == SKINNY
     assert jb.plan(65536, 64, 32)["kernel"] == SKINNY and jb.plan(262144, 32, 16)["kernel"] == SKINNY_TEAM  # 16 < N <= 32: shared-memory variant
     assert jb.plan(4096, 64, 64)["kernel"] != SKINNY and jb.plan(65536, 256, 64)["kernel"] != SKINNY and jb.plan(65536, 64, 128)["kernel"] != SKINNY

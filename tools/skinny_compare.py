@@ -15,7 +15,7 @@ jb.init(0)
 names = jb.kernel_names()
 tile = {n: jb.EXPLICIT_BASE + i for i, n in enumerate(names) if n in ("dmma_tma_f64_64x32x32_s4_x2", "dmma_tma_f64_64x64x32_s3_x2", "dmma_tma_f64_64x64x64_s3")}
 skinny = jb.EXPLICIT_BASE + names.index("dmma_skinny_f64_16x64_xres_w12")
-xreg = jb.EXPLICIT_BASE + names.index("dmma_skinny_f64_16x32_xreg_w8")
+xreg = jb.EXPLICIT_BASE + names.index("dmma_skinny_f64_16x16_xreg_w8")
 team = jb.EXPLICIT_BASE + names.index("dmma_skinny_f64_16x16_xreg_team_w16")
 
 
