@@ -845,10 +845,10 @@ static int make_plan(int dtype, int64_t M, int64_t K, int64_t N, int64_t lda, in
         // one-tile warps: 262144 x 16 x 32 in 18.0 us against 22.2), and it stays at the algorithmic DRAM traffic for any M (10^6
         // rows: 248 us against 293 for private boxes, 253 for the shared-memory variant); for 16 < N <= 32 the shared-memory variant's
         // 4-tile configuration is as fast or faster at every M (65536 x 32 x 64: 13.0 us against 12.7 / 14.9 for the team widths tried)
-        // While A fits in L2 (48 MB here) the private-box variant is ~1 us faster: the four quarter-column warps of a row block
+        // While A fits in L2 (up to 72 MB: 131072 x 64 x 64 still measures 35.8 against 36.6 us) the private-box variant is ~1 us faster: the four quarter-column warps of a row block
         // re-fetch its box from L2, not from DRAM, and need no hand-shake (65536 x 64 x 64: 19.9 against 20.8 us, 32768 rows: 11.7
         // against 12.8); beyond that the re-fetches go to DRAM (10^6 rows: 512 us) and the team kernel takes over.
-        if (skinny_xreg_shape_ok(M, N, K) && N > 32 && K == 64 && (double)M * (double)K * 8.0 <= 48.0e6) best = kSkinnyXregKernel;  // (K = 32: team 23.8 vs 24.9 us)
+        if (skinny_xreg_shape_ok(M, N, K) && N > 32 && K == 64 && (double)M * (double)K * 8.0 <= 72.0e6) best = kSkinnyXregKernel;  // (K = 32: team 23.8 vs 24.9 us)
         else if (skinny_xreg_shape_ok(M, N, K) && (N > 32 || N <= 16)) best = kSkinnyTeamKernel;
         else if (skinny_shape_ok(M, N, K)) best = kSkinnyKernel;
     }

@@ -173,7 +173,7 @@ def test_planner_tall_skinny_rules(jb):
     team, xres, xreg = "dmma_skinny_f64_16x16_xreg_team_w16", "dmma_skinny_f64_16x64_xres_w12", "dmma_skinny_f64_16x16_xreg_w8"
     assert jb.plan(65536, 64, 64)["kernel"] == xreg and jb.plan(40000, 64, 48)["kernel"] == xreg  # A fits in L2: private boxes
     assert jb.plan(131072, 32, 48)["kernel"] == team
-    assert jb.plan(131072, 64, 64)["kernel"] == team and jb.plan(1 << 20, 64, 64)["kernel"] == team
+    assert jb.plan(131072, 64, 64)["kernel"] == xreg and jb.plan(300000, 64, 64)["kernel"] == team and jb.plan(1 << 20, 64, 64)["kernel"] == team
     assert jb.plan(65536, 64, 32)["kernel"] == xres and jb.plan(262144, 32, 9)["kernel"] == team and jb.plan(65536, 72, 48)["kernel"] == xres
     for shape in [(4096, 64, 64), (65536, 256, 64), (65536, 64, 128), (65535, 64, 64), (65536, 36, 64)]:
         assert "skinny" not in jb.plan(*shape)["kernel"], shape
