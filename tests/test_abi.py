@@ -178,3 +178,19 @@ def test_planner_tall_skinny_rules(jb):
     for shape in [(4096, 64, 64), (65536, 256, 64), (65536, 64, 128), (65535, 64, 64), (65536, 36, 64)]:
         assert "skinny" not in jb.plan(*shape)["kernel"], shape
     assert "skinny" not in jb.plan(65536, 64, 64, kernel=jb.F64_SIMT)["kernel"]
+
+
+def test_documented_kernel_names_exist(jb):
+    """Every full kernel name quoted in DESIGN.md / README.md / INTEGRATION.md is (a prefix of) a registered kernel: the documents
+    must not drift from the registry the planner and the explicit selectors use."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set(jb.kernel_names())
+    missing = []
+    for fn in ("DESIGN.md", "README.md", "INTEGRATION.md"):
+        with open(os.path.join(root, fn)) as f:
+            for n in re.findall(r"`((?:dmma|simt|tf32x3)_[a-z0-9_]+)`", f.read()):
+                if n not in names and not any(k.startswith(n) for k in names):
+                    missing.append((fn, n))
+    assert not missing, sorted(set(missing))
