@@ -194,3 +194,24 @@ def test_documented_kernel_names_exist(jb):
                 if n not in names and not any(k.startswith(n) for k in names):
                     missing.append((fn, n))
     assert not missing, sorted(set(missing))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` needs no GPU: ONE JSON line on stdout with the contract keys of the reference arm -- the CPU
+    restatement of the jmul! loop nest timed on a bounded slab of the same workload (the only other place bench.py may execute oracle/)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=240, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "TFLOP/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["metric"].startswith("GEMM TFLOP/s") and "8192" in d["config"]["workload"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
